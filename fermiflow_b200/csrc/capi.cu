@@ -1,0 +1,190 @@
+// C ABI of fermiflow_b200 (see include/fermiflow_b200.h).  Host-side launch planning only;
+// all arithmetic is in the kernels.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/fermiflow_b200.h"
+#include "ff_adjoint.cuh"
+#include "ff_flow.cuh"
+#include "ff_misc.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define FF_CUDA(call)                                         \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+struct DevInfo { int sms = 0; int smem_optin = 0; bool ok = false; };
+DevInfo dev_info() {
+    static thread_local DevInfo di[16];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DevInfo& d = di[dev & 15];
+    if (!d.ok) {
+        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        d.ok = true;
+    }
+    return d;
+}
+
+int check_model(const ff_model* m) {
+    if (!m) return fail(-1, "model is null");
+    const int n = m->n_up + m->n_dn;
+    if (m->n_up < 0 || m->n_dn < 0 || n < 1) return fail(-1, "bad particle numbers %d/%d", m->n_up, m->n_dn);
+    if (n > 200) return fail(-1, "n = %d particles exceeds the supported 200", n);
+    if (m->H_eta < 1 || m->H_mu < 0) return fail(-1, "bad hidden sizes");
+    if (m->nsteps < 1) return fail(-1, "nsteps must be >= 1");
+    if (!m->eta_w1 || !m->eta_b1 || !m->eta_w2) return fail(-1, "eta parameters missing");
+    if (m->H_mu > 0 && (!m->mu_w1 || !m->mu_b1 || !m->mu_w2)) return fail(-1, "mu parameters missing");
+    return 0;
+}
+
+inline int even(int x) { return (x + 1) & ~1; }
+
+// Fills the geometry fields of FlowArgs and returns threads / dynamic smem bytes.
+int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t& smem) {
+    const DevInfo di = dev_info();
+    const int n = m->n_up + m->n_dn;
+    a.n = n; a.n_up = m->n_up; a.H_eta = m->H_eta; a.H_mu = m->H_mu;
+    a.eta_w1 = m->eta_w1; a.eta_b1 = m->eta_b1; a.eta_w2 = m->eta_w2;
+    a.mu_w1 = m->mu_w1; a.mu_b1 = m->mu_b1; a.mu_w2 = m->mu_w2;
+    a.nsteps = m->nsteps;
+    a.D = 2 * n;
+    a.NP = n * (n - 1) / 2;
+    a.P = a.NP + (m->H_mu > 0 ? n : 0);
+    if (a.P < 1) return fail(-1, "a single particle without one-body backflow has no velocity field");
+    const bool eloc = mode == ff::MODE_ELOC;
+    a.DP = eloc ? ((a.D + 3) / 4) * 4 + 2 : a.D;
+    a.NSV = eloc ? 3 * a.D + 2 + a.D * a.DP : a.D + (mode >= ff::MODE_DIV ? 1 : 0);
+    int off = even(5 * a.NSV);
+    a.off_G = off; off = even(off + a.P * ff::kGRec);
+    a.off_AM = off; if (eloc) off = even(off + a.D * a.DP);
+    a.off_u = off; if (eloc) off += a.D;
+    a.off_kLx = off; if (eloc) off += a.D;
+    a.off_part = off; off = even(off + 2 * n);
+    a.off_x0 = off; if (eloc) off += a.D;
+    a.off_sl = a.NSV;
+    a.wstride = even(off);
+    if (eloc) {
+        const int need = ff::slater_scratch_size(m->n_up, m->n_dn) + 2 * a.D + n * n + a.NP + 8;
+        if (need > 4 * a.NSV) return fail(-2, "internal: finale scratch does not fit");
+    }
+    int common = 64 + 6 * (m->H_eta + m->H_mu);
+    common = even(common) + 2 * ((a.NP + 7) / 8) + 2;
+    const long long budget = (long long)di.smem_optin / 8 - common;
+    const int target_threads = eloc ? 512 : 256;
+    int W = (int)(budget / a.wstride);
+    if (W > target_threads / a.P) W = target_threads / a.P;
+    if (a.P > 512) return fail(-2, "n = %d needs %d threads per walker (> 512)", n, a.P);
+    if (W < 1) {
+        if (budget / a.wstride < 1)
+            return fail(-2, "n = %d needs %lld bytes of shared memory per walker, device allows %d",
+                        n, (long long)(a.wstride + common) * 8, di.smem_optin);
+        W = 1;
+    }
+    a.W = W;
+    threads = ((W * a.P + 31) / 32) * 32;
+    if (threads < 64) threads = 64;
+    smem = (size_t)(common + (long long)W * a.wstride) * 8;
+    return 0;
+}
+
+template <int MODE>
+int launch_flow(ff::FlowArgs& a, int threads, size_t smem, cudaStream_t st) {
+    const DevInfo di = dev_info();
+    FF_CUDA(cudaFuncSetAttribute(ff::flow_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ff::flow_kernel<MODE>, threads, smem));
+    if (occ < 1) return fail(-2, "flow kernel does not fit on an SM (threads %d, smem %zu)", threads, smem);
+    long long nb = (a.B + a.W - 1) / a.W;
+    long long grid = (long long)di.sms * occ;
+    if (grid > nb) grid = nb;
+    if (grid < 1) return 0;
+    ff::flow_kernel<MODE><<<(unsigned)grid, threads, smem, st>>>(a);
+    FF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ff_version(void) { return 100; }
+const char* ff_last_error(void) { return g_err; }
+
+int ff_stash_sizes(const ff_model* m, long long B, long long* ny, long long* nc) {
+    if (int e = check_model(m)) return e;
+    const long long n = m->n_up + m->n_dn, NS = 4LL * m->nsteps;
+    const long long P = n * (n - 1) / 2 + (m->H_mu > 0 ? n : 0);
+    if (ny) *ny = B * NS * 2 * n;
+    if (nc) *nc = B * NS * P * 3;
+    return 0;
+}
+
+int ff_cnf_generate(const ff_model* m, const double* z, long long B, int reverse, double* x, void* stream) {
+    if (int e = check_model(m)) return e;
+    if (B < 0 || (B > 0 && (!z || !x))) return fail(-1, "ff_cnf_generate: null buffer");
+    ff::FlowArgs a{};
+    int threads; size_t smem;
+    if (int e = plan_flow(ff::MODE_V, m, a, threads, smem)) return e;
+    a.ta = reverse ? m->t1 : m->t0; a.tb = reverse ? m->t0 : m->t1;
+    a.B = B; a.x_in = z; a.y_out = x;
+    return launch_flow<ff::MODE_V>(a, threads, smem, (cudaStream_t)stream);
+}
+
+int ff_cnf_delta_logp(const ff_model* m, const double* x, long long B, double* z, double* delta_logp,
+                      double* stash_y, double* stash_c, void* stream) {
+    if (int e = check_model(m)) return e;
+    if (B < 0 || (B > 0 && !x)) return fail(-1, "ff_cnf_delta_logp: null input");
+    const bool stash = stash_y || stash_c;
+    if (stash && !(stash_y && stash_c)) return fail(-1, "ff_cnf_delta_logp: give both stash arrays or none");
+    ff::FlowArgs a{};
+    int threads; size_t smem;
+    const int mode = stash ? ff::MODE_STASH : ff::MODE_DIV;
+    if (int e = plan_flow(mode, m, a, threads, smem)) return e;
+    a.ta = m->t1; a.tb = m->t0;
+    a.B = B; a.x_in = x; a.y_out = z; a.delta_out = delta_logp;
+    a.stash_y = stash_y; a.stash_c = stash_c;
+    return stash ? launch_flow<ff::MODE_STASH>(a, threads, smem, (cudaStream_t)stream)
+                 : launch_flow<ff::MODE_DIV>(a, threads, smem, (cudaStream_t)stream);
+}
+
+int ff_eloc(const ff_model* m, const double* x, long long B, const int* orb, const int* walker_state,
+            double Z, int harmonic, double* z, double* delta_logp, double* logp, double* grad,
+            double* lap, double* kinetic, double* potential, double* eloc,
+            double* stash_y, double* stash_c, void* stream) {
+    if (int e = check_model(m)) return e;
+    if (B < 0 || (B > 0 && (!x || !orb))) return fail(-1, "ff_eloc: null input");
+    if ((stash_y != nullptr) != (stash_c != nullptr)) return fail(-1, "ff_eloc: give both stash arrays or none");
+    ff::FlowArgs a{};
+    int threads; size_t smem;
+    if (int e = plan_flow(ff::MODE_ELOC, m, a, threads, smem)) return e;
+    a.ta = m->t1; a.tb = m->t0;
+    a.B = B; a.x_in = x; a.y_out = z; a.delta_out = delta_logp;
+    a.stash_y = stash_y; a.stash_c = stash_c;
+    a.orb = orb; a.walker_state = walker_state; a.Z = Z; a.harmonic = harmonic;
+    a.logp = logp; a.grad = grad; a.lap = lap; a.kin = kinetic; a.pot = potential; a.eloc = eloc;
+    return launch_flow<ff::MODE_ELOC>(a, threads, smem, (cudaStream_t)stream);
+}
+
+#include "capi_rest.inc"
+
+}  // extern "C"

@@ -1,0 +1,501 @@
+// Fixed-step (3/8-rule RK4) continuous normalizing flow of fermion coordinates, with
+// optional divergence integral, adjoint stash, and the forward-mode (Jacobian + Laplacian)
+// propagation that yields grad/laplacian of log p and the local energy in ONE sweep.
+//
+// Replaces, for dim = 2 and D_in = 1 MLPs:
+//   flow.py:42-56 CNF.generate / CNF.delta_logp (via NeuralODE/nnModule.py:151 solve_ivp),
+//   equivariant_funs.py:17-102 Backflow forward / divergence,
+//   utils.py:44-65 y_grad_laplacian (2N nested autograd passes -> forward-mode here),
+//   VMC.py:41-55 GSVMC.forward's kinetic + potential energy.
+#pragma once
+#include "ff_common.cuh"
+#include "ff_slater.cuh"
+
+namespace ff {
+
+enum FlowMode { MODE_V = 0, MODE_DIV = 1, MODE_STASH = 2, MODE_ELOC = 3 };
+
+struct FlowArgs {
+    // model
+    int n, n_up, H_eta, H_mu;
+    const double *eta_w1, *eta_b1, *eta_w2, *mu_w1, *mu_b1, *mu_w2;
+    double ta, tb;          // integrate from ta to tb
+    int nsteps;
+    // batch
+    long long B;
+    const double* x_in;     // [B][n][2]
+    double* y_out;          // [B][n][2]   end point of the flow
+    double* delta_out;      // [B]         integral of -div v  (MODE >= DIV)
+    // adjoint stash (MODE >= STASH, nullable)
+    double* stash_y;        // [B][4*nsteps][D]
+    double* stash_c;        // [B][4*nsteps][P][3]   eta, eta', eta'' (or mu...) per item
+    // MODE_ELOC
+    const int* orb;         // occupation table, rows of n orbital ids (up block then down)
+    const int* walker_state;// [B] row of `orb` per walker, or null (row 0 for everybody)
+    double Z;               // Coulomb strength
+    int harmonic;           // add 1/2 r^2
+    double *logp, *grad, *lap, *kin, *pot, *eloc;
+    // launch geometry (host-computed)
+    int W;                  // walkers per CTA
+    int P, NP;              // items per walker (pairs + singles), pairs
+    int D, DP;              // 2n, padded row length of J
+    int NSV;                // state doubles per walker
+    int wstride;            // shared doubles per walker
+    int off_G, off_AM, off_u, off_kLx, off_part, off_x0, off_sl;   // offsets inside a walker block
+};
+
+// State vector layout (MODE_ELOC): [y:D][L:D][gD:D][Delta, lapDelta][J: D x DP]
+// otherwise:                        [y:D][Delta]
+
+// Base-distribution end of the E_loc sweep (MODE_ELOC): at z = flow^-1(x) evaluate
+// log p0 = 2 (log|det_up| + log|det_dn|) (base_dist.py:48-56) with gradient g0 and the
+// Hessian contraction <H0, J J^T>, then assemble
+//   log p = log p0 - Delta,  grad = J^T g0 - gDelta,  lap = <H0, JJ^T> + g0.L - lapDelta,
+//   E_loc = -1/4 lap - 1/8 |grad|^2 + V(x)                       (VMC.py:48-55).
+__device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
+                            const unsigned char* pair_i, const unsigned char* pair_j) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int n = a.n, D = a.D, DP = a.DP, W = a.W, NP = a.NP;
+    const int oL = D, oG = 2 * D, oS = 3 * D, oJ = 3 * D + 2;
+    auto S_in = [&](int w) { return wbase + (size_t)w * a.wstride; };
+    auto scr = [&](int w) { return S_in(w) + a.off_sl; };
+    const int slsz = slater_scratch_size(a.n_up, n - a.n_up);
+    // scratch tail: g0[D], red[n*n + NP + 8]
+    auto g0p = [&](int w) { return scr(w) + slsz; };
+    auto red = [&](int w) { return scr(w) + slsz + D; };
+
+    slater_team<true>(W, n, a.n_up,
+        [&](int w) { return (const double*)S_in(w); }, scr,
+        [&](int w) { long long b = base + w; int row = (a.walker_state && b < a.B) ? a.walker_state[b] : 0;
+                     return a.orb + (size_t)row * n; });
+
+    // M = J J^T at the end point (upper blocks), into the AM buffer
+    {
+        const int ntile = n * (n + 1) / 2;
+        for (int g = tid; g < W * ntile; g += T) {
+            int w = g / ntile, t = g - w * ntile;
+            int i, j;
+            if (t < NP) { i = pair_i[t]; j = pair_j[t]; } else { i = j = t - NP; }
+            const double* J = S_in(w) + oJ;
+            const double* a0 = J + (2 * i) * DP; const double* a1 = a0 + DP;
+            const double* b0 = J + (2 * j) * DP; const double* b1 = b0 + DP;
+            double m00 = 0, m01 = 0, m10 = 0, m11 = 0;
+            for (int c = 0; c < D; ++c) {
+                m00 = fma(a0[c], b0[c], m00); m01 = fma(a0[c], b1[c], m01);
+                m10 = fma(a1[c], b0[c], m10); m11 = fma(a1[c], b1[c], m11);
+            }
+            double* M = S_in(w) + a.off_AM;
+            M[(2 * i) * DP + 2 * j] = m00; M[(2 * i) * DP + 2 * j + 1] = m01;
+            M[(2 * i + 1) * DP + 2 * j] = m10; M[(2 * i + 1) * DP + 2 * j + 1] = m11;
+        }
+    }
+    // g0 and the per-(i,j) Hessian contraction terms
+    for (int s = 0; s < 2; ++s) {
+        const SlBlk blk = slater_blk(s, n, a.n_up);
+        const int ns = blk.ns;
+        for (int g = tid; g < W * ns; g += T) {
+            int w = g / ns, i = g - w * ns;
+            const double* S = scr(w);
+            g0p(w)[2 * (blk.i0 + i)] = 2.0 * S[blk.bx() + i * ns + i];
+            g0p(w)[2 * (blk.i0 + i) + 1] = 2.0 * S[blk.by() + i * ns + i];
+        }
+    }
+    __syncthreads();
+    for (int g = tid; g < W * n * n; g += T) {
+        int w = g / (n * n), rem = g - w * n * n;
+        int I = rem / n, Jp = rem - I * n;
+        const int sI = I >= a.n_up, sJ = Jp >= a.n_up;
+        double t = 0.0;
+        if (sI == sJ) {
+            const SlBlk blk = slater_blk(sI, n, a.n_up);
+            const int ns = blk.ns, i = I - blk.i0, j = Jp - blk.i0;
+            const double* S = scr(w);
+            const double* M = S_in(w) + a.off_AM;
+            const double bxij = S[blk.bx() + i * ns + j], byij = S[blk.by() + i * ns + j];
+            const double bxji = S[blk.bx() + j * ns + i], byji = S[blk.by() + j * ns + i];
+            double m00, m01, m10, m11;       // M[(2I+a)][(2J+b)]
+            if (I <= Jp) {
+                m00 = M[(2 * I) * DP + 2 * Jp]; m01 = M[(2 * I) * DP + 2 * Jp + 1];
+                m10 = M[(2 * I + 1) * DP + 2 * Jp]; m11 = M[(2 * I + 1) * DP + 2 * Jp + 1];
+            } else {
+                m00 = M[(2 * Jp) * DP + 2 * I]; m10 = M[(2 * Jp) * DP + 2 * I + 1];
+                m01 = M[(2 * Jp + 1) * DP + 2 * I]; m11 = M[(2 * Jp + 1) * DP + 2 * I + 1];
+            }
+            t = -(bxij * bxji * m00 + bxij * byji * m01 + byij * bxji * m10 + byij * byji * m11);
+            if (I == Jp) {
+                const double* C = S + blk.cc() + 3 * i;
+                t += C[0] * m00 + 2.0 * C[1] * m01 + C[2] * m11;
+            }
+        }
+        red(w)[rem] = t;
+    }
+    // Coulomb terms at the original coordinates
+    for (int g = tid; g < W * NP; g += T) {
+        int w = g / NP, p = g - w * NP;
+        const double* x0 = S_in(w) + a.off_x0;
+        const int i = pair_i[p], j = pair_j[p];
+        const double dx = x0[2 * i] - x0[2 * j], dy = x0[2 * i + 1] - x0[2 * j + 1];
+        red(w)[n * n + p] = a.Z / sqrt(fma(dx, dx, dy * dy));
+    }
+    __syncthreads();
+    // grad[c] = sum_r g0[r] J[r][c] - gDelta[c]   (kept in the KK area is dead: write to P3 slot 0..D)
+    for (int g = tid; g < W * D; g += T) {
+        int w = g / D, c = g - w * D;
+        const double* J = S_in(w) + oJ + c;
+        const double* g0 = g0p(w);
+        double acc = -S_in(w)[oG + c];
+        for (int r = 0; r < D; ++r) acc = fma(g0[r], J[r * DP], acc);
+        red(w)[n * n + NP + 8 + c] = acc;
+        long long b = base + w;
+        if (b < a.B && a.grad) a.grad[b * D + c] = acc;
+    }
+    __syncthreads();
+    for (int w = tid; w < W; w += T) {
+        long long b = base + w;
+        if (b >= a.B) continue;
+        const double* Sw = S_in(w);
+        const double* S = scr(w);
+        double lap0 = 0.0, vc = 0.0, g2 = 0.0, gl = 0.0, vh = 0.0;
+        const double* r = red(w);
+        for (int k = 0; k < n * n; ++k) lap0 += r[k];
+        for (int k = 0; k < NP; ++k) vc += r[n * n + k];
+        for (int k = 0; k < D; ++k) {
+            const double gk = r[n * n + NP + 8 + k];
+            g2 = fma(gk, gk, g2);
+            gl = fma(g0p(w)[k], Sw[oL + k], gl);
+            const double xk = (Sw + a.off_x0)[k];
+            vh = fma(xk, xk, vh);
+        }
+        const SlBlk bu = slater_blk(0, n, a.n_up), bd = slater_blk(1, n, a.n_up);
+        double ld = 0.0;
+        if (bu.ns) ld += S[bu.misc() + 2];
+        if (bd.ns) ld += S[bd.misc() + 2];
+        const double lp = 2.0 * ld - Sw[oS];
+        const double lap = 2.0 * lap0 + gl - Sw[oS + 1];
+        const double kin = -0.25 * lap - 0.125 * g2;
+        const double pot = vc + (a.harmonic ? 0.5 * vh : 0.0);
+        if (a.logp) a.logp[b] = lp;
+        if (a.lap) a.lap[b] = lap;
+        if (a.kin) a.kin[b] = kin;
+        if (a.pot) a.pot[b] = pot;
+        if (a.eloc) a.eloc[b] = kin + pot;
+    }
+    __syncthreads();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int n = a.n, D = a.D, DP = a.DP, P = a.P, NP = a.NP, W = a.W, NSV = a.NSV;
+    (void)DP;
+    const bool has_mu = a.H_mu > 0;
+
+    // ---- shared carve-up -------------------------------------------------------------
+    double* tab = smem;                               // 64
+    double* coef_eta = tab + 64;                      // 6 H_eta
+    double* coef_mu = coef_eta + 6 * a.H_eta;         // 6 H_mu
+    int cbase = 64 + 6 * (a.H_eta + a.H_mu);
+    cbase = (cbase + 1) & ~1;
+    unsigned char* pair_i = reinterpret_cast<unsigned char*>(smem + cbase);   // NP each
+    unsigned char* pair_j = pair_i + ((NP + 7) & ~7);
+    double* wbase = smem + cbase + 2 * ((NP + 7) / 8);
+    if ((wbase - smem) & 1) wbase += 1;
+
+    for (int i = tid; i < 64; i += T) tab[i] = c_exp2_64[i];
+    load_mlp_coef(coef_eta, a.eta_w1, a.eta_b1, a.eta_w2, a.H_eta);
+    if (has_mu) load_mlp_coef(coef_mu, a.mu_w1, a.mu_b1, a.mu_w2, a.H_mu);
+    for (int p = tid; p < NP; p += T) {
+        int i = 0, rem = p;
+        while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+        pair_i[p] = (unsigned char)i;
+        pair_j[p] = (unsigned char)(i + 1 + rem);
+    }
+
+    const double h = (a.tb - a.ta) / a.nsteps;
+    const int NS = 4 * a.nsteps;
+
+    // per-walker block pointers
+    auto S_in = [&](int w) { return wbase + (size_t)w * a.wstride; };
+    auto P3 = [&](int w) { return S_in(w) + NSV; };
+    auto P4 = [&](int w) { return S_in(w) + 2 * NSV; };
+    auto PO = [&](int w) { return S_in(w) + 3 * NSV; };
+    auto KK = [&](int w) { return S_in(w) + 4 * NSV; };
+    auto GG = [&](int w) { return S_in(w) + a.off_G; };
+    constexpr int oY = 0;
+    const int oL = D, oG = 2 * D, oS = 3 * D, oJ = 3 * D + 2;       // ELOC offsets
+    const int oDelta = (MODE == MODE_ELOC) ? oS : D;
+
+    // item owned by this thread
+    const int it_w = tid / P, it_p = tid - it_w * P;
+    const bool it_valid = it_w < W;
+    const bool it_pair = it_p < NP;
+    int it_i = 0, it_j = 0;
+
+    for (long long base = (long long)blockIdx.x * W; base < a.B; base += (long long)gridDim.x * W) {
+        __syncthreads();
+        if (it_valid) {
+            if (it_pair) { it_i = pair_i[it_p]; it_j = pair_j[it_p]; }
+            else { it_i = it_p - NP; it_j = it_i; }
+        }
+        // ---- load walkers, initialise state -------------------------------------------
+        for (int g = tid; g < W * NSV; g += T) {
+            int w = g / NSV, e = g - w * NSV;
+            long long b = base + w;
+            double v = 0.0;
+            if (e < D) {
+                // padding walkers get a harmless, well separated configuration
+                v = (b < a.B) ? a.x_in[b * D + e] : (double)(e >> 1) + 0.37 * (e & 1);
+            } else if (MODE == MODE_ELOC && e >= oJ) {
+                int r = (e - oJ) / DP, c = (e - oJ) - r * DP;
+                v = (r == c) ? 1.0 : 0.0;
+            }
+            S_in(w)[e] = v;
+            if (MODE == MODE_ELOC && e < D) (S_in(w) + a.off_x0)[e] = v;
+        }
+        __syncthreads();
+
+        for (int stage = 0; stage < NS; ++stage) {
+            const int sub = stage & 3;
+            // ======== S0: per-item radial functions (+ SYRK for ELOC) =====================
+            double rx = 0, ry = 0, ca = 0, cb = 0, ccq = 0, ceq = 0, cf = 0;
+            if (it_valid) {
+                const double* y = S_in(it_w) + oY;
+                if (it_pair) { rx = y[2 * it_i] - y[2 * it_j]; ry = y[2 * it_i + 1] - y[2 * it_j + 1]; }
+                else { rx = y[2 * it_i]; ry = y[2 * it_i + 1]; }
+                const double d2 = fma(rx, rx, ry * ry);
+                const double d = sqrt(d2);
+                double f[4];
+                constexpr int ORD = (MODE == MODE_V) ? 0 : (MODE == MODE_DIV) ? 1 : (MODE == MODE_STASH) ? 2 : 3;
+                if (it_pair) radial_mlp<ORD>(coef_eta, a.H_eta, d, tab, f);
+                else radial_mlp<ORD>(coef_mu, a.H_mu, d, tab, f);
+                double* G = GG(it_w) + it_p * kGRec;
+                cf = f[0];
+                G[0] = cf * rx;
+                G[1] = cf * ry;
+                if (MODE >= MODE_DIV) {
+                    const double mult = it_pair ? 2.0 : 1.0;
+                    G[6] = mult * fma(f[1], d, 2.0 * f[0]);                 // q
+                }
+                if (MODE >= MODE_STASH && a.stash_c != nullptr) {
+                    long long b = base + it_w;
+                    if (b < a.B) {
+                        double* sc = a.stash_c + ((b * NS + stage) * P + it_p) * 3;
+                        sc[0] = f[0]; sc[1] = f[1]; sc[2] = f[2];
+                    }
+                }
+                if (MODE == MODE_ELOC) {
+                    const double mult = it_pair ? 2.0 : 1.0;
+                    const double inv_d = 1.0 / d, inv_d2 = inv_d * inv_d;
+                    ca = f[1] * inv_d;                                       // f'/d
+                    cb = (f[2] - ca) * inv_d2;                               // (f'' - f'/d)/d^2
+                    const double q1 = mult * fma(f[2], d, 3.0 * f[1]);       // q'
+                    const double q2 = mult * fma(f[3], d, 4.0 * f[2]);       // q''
+                    ccq = q1 * inv_d;
+                    ceq = (q2 - ccq) * inv_d2;
+                    G[2] = ccq * rx;
+                    G[3] = ccq * ry;
+                    G[8] = fma(ca * rx, rx, cf);
+                    G[9] = ca * rx * ry;
+                    G[10] = fma(ca * ry, ry, cf);
+                }
+            }
+            if (MODE >= MODE_STASH && a.stash_y != nullptr) {
+                for (int g = tid; g < W * D; g += T) {
+                    int w = g / D, e = g - w * D;
+                    long long b = base + w;
+                    if (b < a.B) a.stash_y[(b * NS + stage) * D + e] = S_in(w)[e];
+                }
+            }
+            if (MODE == MODE_ELOC) {
+                // M = J J^T (upper 2x2 blocks i <= j), one (walker, i, j) tile per loop trip
+                const int ntile = n * (n + 1) / 2;
+                for (int g = tid; g < W * ntile; g += T) {
+                    int w = g / ntile, t = g - w * ntile;
+                    int i, j;
+                    if (t < NP) { i = pair_i[t]; j = pair_j[t]; } else { i = j = t - NP; }
+                    const double* J = S_in(w) + oJ;
+                    const double* a0 = J + (2 * i) * DP; const double* a1 = a0 + DP;
+                    const double* b0 = J + (2 * j) * DP; const double* b1 = b0 + DP;
+                    double m00 = 0, m01 = 0, m10 = 0, m11 = 0;
+                    for (int c = 0; c < D; c += 2) {
+                        double2 x0 = *reinterpret_cast<const double2*>(a0 + c);
+                        double2 x1 = *reinterpret_cast<const double2*>(a1 + c);
+                        double2 z0 = *reinterpret_cast<const double2*>(b0 + c);
+                        double2 z1 = *reinterpret_cast<const double2*>(b1 + c);
+                        m00 = fma(x0.x, z0.x, m00); m00 = fma(x0.y, z0.y, m00);
+                        m01 = fma(x0.x, z1.x, m01); m01 = fma(x0.y, z1.y, m01);
+                        m10 = fma(x1.x, z0.x, m10); m10 = fma(x1.y, z0.y, m10);
+                        m11 = fma(x1.x, z1.x, m11); m11 = fma(x1.y, z1.y, m11);
+                    }
+                    double* M = S_in(w) + a.off_AM;
+                    M[(2 * i) * DP + 2 * j] = m00; M[(2 * i) * DP + 2 * j + 1] = m01;
+                    M[(2 * i + 1) * DP + 2 * j] = m10; M[(2 * i + 1) * DP + 2 * j + 1] = m11;
+                }
+                __syncthreads();
+                // ======== S1: second-derivative contractions per item ====================
+                if (it_valid) {
+                    const double* M = S_in(it_w) + a.off_AM;
+                    const int i2 = 2 * it_i, j2 = 2 * it_j;
+                    double w00, w01, w11;
+                    if (it_pair) {
+                        w00 = M[i2 * DP + i2] + M[j2 * DP + j2] - 2.0 * M[i2 * DP + j2];
+                        w11 = M[(i2 + 1) * DP + i2 + 1] + M[(j2 + 1) * DP + j2 + 1] - 2.0 * M[(i2 + 1) * DP + j2 + 1];
+                        w01 = M[i2 * DP + i2 + 1] + M[j2 * DP + j2 + 1] - M[i2 * DP + j2 + 1] - M[(i2 + 1) * DP + j2];
+                    } else {
+                        w00 = M[i2 * DP + i2]; w01 = M[i2 * DP + i2 + 1]; w11 = M[(i2 + 1) * DP + i2 + 1];
+                    }
+                    const double wrx = fma(w00, rx, w01 * ry), wry = fma(w01, rx, w11 * ry);
+                    const double trw = w00 + w11, rwr = fma(rx, wrx, ry * wry);
+                    double* G = GG(it_w) + it_p * kGRec;
+                    G[4] = fma(ca, fma(2.0, wrx, trw * rx), cb * rwr * rx);
+                    G[5] = fma(ca, fma(2.0, wry, trw * ry), cb * rwr * ry);
+                    G[7] = fma(ccq, trw, ceq * rwr);
+                }
+            }
+            __syncthreads();
+            // ======== S2: gather per particle, build Jacobian matrix ======================
+            {
+                constexpr int NC = (MODE == MODE_ELOC) ? kGRec : (MODE >= MODE_DIV ? 3 : 2);
+                for (int g = tid; g < W * n * NC; g += T) {
+                    int w = g / (n * NC), rem = g - w * (n * NC);
+                    int i = rem / NC, cc = rem - i * NC;
+                    int c = (MODE == MODE_ELOC) ? cc : (cc == 2 ? 6 : cc);
+                    const double* G = GG(w);
+                    double acc = 0.0;
+                    const bool odd = c < 6;
+                    const double wgt = (c == 6 || c == 7) ? 0.5 : 1.0;
+                    for (int j = 0; j < i; ++j) {
+                        double v = G[pair_index(j, i, n) * kGRec + c];
+                        acc += odd ? -v : v;
+                    }
+                    for (int j = i + 1; j < n; ++j) acc += G[pair_index(i, j, n) * kGRec + c];
+                    acc *= wgt;
+                    if (has_mu) acc += G[(NP + i) * kGRec + c];
+                    double* Sw = S_in(w);
+                    if (c < 2) KK(w)[oY + 2 * i + c] = acc;
+                    else if (c < 4) (Sw + a.off_u)[2 * i + c - 2] = acc;
+                    else if (c < 6) (Sw + a.off_kLx)[2 * i + c - 4] = acc;
+                    else if (c < 8) (Sw + a.off_part)[(c - 6) * n + i] = acc;
+                    else {
+                        double* A = Sw + a.off_AM;
+                        if (c == 8) A[(2 * i) * DP + 2 * i] = acc;
+                        else if (c == 9) { A[(2 * i) * DP + 2 * i + 1] = acc; A[(2 * i + 1) * DP + 2 * i] = acc; }
+                        else A[(2 * i + 1) * DP + 2 * i + 1] = acc;
+                    }
+                }
+                if (MODE == MODE_ELOC && it_valid && it_pair) {
+                    double* A = S_in(it_w) + a.off_AM;
+                    const double a00 = -fma(ca * rx, rx, cf), a01 = -(ca * rx * ry), a11 = -fma(ca * ry, ry, cf);
+                    const int i2 = 2 * it_i, j2 = 2 * it_j;
+                    A[i2 * DP + j2] = a00; A[i2 * DP + j2 + 1] = a01;
+                    A[(i2 + 1) * DP + j2] = a01; A[(i2 + 1) * DP + j2 + 1] = a11;
+                    A[j2 * DP + i2] = a00; A[j2 * DP + i2 + 1] = a01;
+                    A[(j2 + 1) * DP + i2] = a01; A[(j2 + 1) * DP + i2 + 1] = a11;
+                }
+            }
+            __syncthreads();
+            // ======== S3: derivative of the whole state ===================================
+            if (MODE == MODE_ELOC) {
+                // K.J = A * J : 2 x 4 register tiles
+                const int ncg = (D + 3) / 4;
+                for (int g = tid; g < W * n * ncg; g += T) {
+                    int w = g / (n * ncg), rem = g - w * (n * ncg);
+                    int i = rem / ncg, cg = rem - i * ncg;
+                    const double* A = S_in(w) + a.off_AM;        // symmetric: column 2i.. read as row
+                    const double* J = S_in(w) + oJ + 4 * cg;
+                    double k00 = 0, k01 = 0, k02 = 0, k03 = 0, k10 = 0, k11 = 0, k12 = 0, k13 = 0;
+#pragma unroll 4
+                    for (int k = 0; k < D; ++k) {
+                        double2 av = *reinterpret_cast<const double2*>(A + k * DP + 2 * i);
+                        double2 b01 = *reinterpret_cast<const double2*>(J + k * DP);
+                        double2 b23 = *reinterpret_cast<const double2*>(J + k * DP + 2);
+                        k00 = fma(av.x, b01.x, k00); k01 = fma(av.x, b01.y, k01);
+                        k02 = fma(av.x, b23.x, k02); k03 = fma(av.x, b23.y, k03);
+                        k10 = fma(av.y, b01.x, k10); k11 = fma(av.y, b01.y, k11);
+                        k12 = fma(av.y, b23.x, k12); k13 = fma(av.y, b23.y, k13);
+                    }
+                    double* K = KK(w) + oJ + (2 * i) * DP + 4 * cg;
+                    *reinterpret_cast<double2*>(K) = make_double2(k00, k01);
+                    *reinterpret_cast<double2*>(K + 2) = make_double2(k02, k03);
+                    *reinterpret_cast<double2*>(K + DP) = make_double2(k10, k11);
+                    *reinterpret_cast<double2*>(K + DP + 2) = make_double2(k12, k13);
+                }
+                // K.L = A L + kLx ;  K.gD = -(u^T J)
+                for (int g = tid; g < W * 2 * D; g += T) {
+                    int w = g / (2 * D), e = g - w * 2 * D;
+                    const double* Sw = S_in(w);
+                    if (e < D) {
+                        const double* A = Sw + a.off_AM + e * DP;
+                        const double* L = Sw + oL;
+                        double acc = (Sw + a.off_kLx)[e];
+                        for (int k = 0; k < D; ++k) acc = fma(A[k], L[k], acc);
+                        KK(w)[oL + e] = acc;
+                    } else {
+                        int c = e - D;
+                        const double* u = Sw + a.off_u;
+                        const double* J = Sw + oJ + c;
+                        double acc = 0.0;
+                        for (int k = 0; k < D; ++k) acc = fma(u[k], J[k * DP], acc);
+                        KK(w)[oG + c] = -acc;
+                    }
+                }
+                for (int w = tid; w < W; w += T) {
+                    const double* Sw = S_in(w);
+                    const double* part = Sw + a.off_part;
+                    double rho = 0.0, lp = 0.0;
+                    for (int i = 0; i < n; ++i) { rho += part[i]; lp += part[n + i]; }
+                    const double* u = Sw + a.off_u; const double* L = Sw + oL;
+                    for (int k = 0; k < D; ++k) lp = fma(u[k], L[k], lp);
+                    KK(w)[oS] = -rho;
+                    KK(w)[oS + 1] = -lp;
+                }
+            } else if (MODE >= MODE_DIV) {
+                for (int w = tid; w < W; w += T) {
+                    const double* part = S_in(w) + a.off_part;
+                    double rho = 0.0;
+                    for (int i = 0; i < n; ++i) rho += part[i];
+                    KK(w)[oDelta] = -rho;
+                }
+            }
+            __syncthreads();
+            // ======== S4: 3/8-rule RK4 bookkeeping (torchdiffeq rk4_alt_step_func) ========
+            for (int g = tid; g < W * NSV; g += T) {
+                int w = g / NSV, e = g - w * NSV;
+                double* s = S_in(w) + e;
+                const double k = KK(w)[e] * h;
+                if (sub == 0) {
+                    const double y0 = *s;
+                    P3(w)[e] = fma(k, -1.0 / 3.0, y0);
+                    P4(w)[e] = y0 + k;
+                    PO(w)[e] = fma(k, 0.125, y0);
+                    *s = fma(k, 1.0 / 3.0, y0);
+                } else if (sub == 1) {
+                    *s = P3(w)[e] + k;
+                    P4(w)[e] -= k;
+                    PO(w)[e] = fma(k, 0.375, PO(w)[e]);
+                } else if (sub == 2) {
+                    *s = P4(w)[e] + k;
+                    PO(w)[e] = fma(k, 0.375, PO(w)[e]);
+                } else {
+                    *s = fma(k, 0.125, PO(w)[e]);
+                }
+            }
+            __syncthreads();
+        }   // stages
+
+        // ---- outputs ----------------------------------------------------------------------
+        for (int g = tid; g < W * D; g += T) {
+            int w = g / D, e = g - w * D;
+            long long b = base + w;
+            if (b < a.B && a.y_out) a.y_out[b * D + e] = S_in(w)[e];
+        }
+        if (MODE >= MODE_DIV) {
+            for (int w = tid; w < W; w += T)
+                if (base + w < a.B && a.delta_out) a.delta_out[base + w] = S_in(w)[oDelta];
+        }
+        if (MODE == MODE_ELOC) eloc_finale(a, base, wbase, pair_i, pair_j);
+    }
+}
+
+}  // namespace ff
