@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 
 #include "../../include/fermiflow_b200.h"
 #include "ff_adjoint.cuh"

@@ -1,6 +1,347 @@
+// Stand-alone stages of the path: backflow evaluation, Slater log|det| with derivatives,
+// the Metropolis sampler of the free-fermion base distribution, potentials, Boltzmann
+// occupation sampling and an FP64 throughput probe.
 #pragma once
 #include "ff_common.cuh"
+#include "ff_slater.cuh"
+
 namespace ff {
+
+// ---------------------------------------------------------------------------------------
+// Backflow.forward / Backflow.divergence (equivariant_funs.py:80-102) at given x.
+// One CTA handles W walkers, one thread per (walker, pair | particle) item.
+// ---------------------------------------------------------------------------------------
+struct BackflowArgs {
+    int n, H_eta, H_mu;
+    const double *eta_w1, *eta_b1, *eta_w2, *mu_w1, *mu_b1, *mu_w2;
+    long long B;
+    const double* x;
+    double* v;      // nullable
+    double* div;    // nullable
+    int W, P, NP;
+};
+
+__global__ void __launch_bounds__(512) backflow_kernel(const BackflowArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int n = a.n, D = 2 * n, P = a.P, NP = a.NP, W = a.W;
+    const bool has_mu = a.H_mu > 0;
+    double* tab = smem;
+    double* coef_eta = tab + 64;
+    double* coef_mu = coef_eta + 6 * a.H_eta;
+    double* wb = coef_mu + 6 * a.H_mu;
+    const int wstride = D + 3 * P;          // x[D], G[P][3] (vx, vy, q)
+    for (int i = tid; i < 64; i += T) tab[i] = c_exp2_64[i];
+    load_mlp_coef(coef_eta, a.eta_w1, a.eta_b1, a.eta_w2, a.H_eta);
+    if (has_mu) load_mlp_coef(coef_mu, a.mu_w1, a.mu_b1, a.mu_w2, a.H_mu);
+    const int it_w = tid / P, it_p = tid - it_w * P;
+    for (long long base = (long long)blockIdx.x * W; base < a.B; base += (long long)gridDim.x * W) {
+        __syncthreads();
+        for (int g = tid; g < W * D; g += T) {
+            int w = g / D, e = g - w * D;
+            long long b = base + w;
+            (wb + (size_t)w * wstride)[e] = (b < a.B) ? a.x[b * D + e] : (double)(e >> 1) + 0.37 * (e & 1);
+        }
+        __syncthreads();
+        if (it_w < W) {
+            const double* x = wb + (size_t)it_w * wstride;
+            double* G = wb + (size_t)it_w * wstride + D + 3 * it_p;
+            double rx, ry;
+            const bool pair = it_p < NP;
+            if (pair) {
+                int i = 0, rem = it_p;
+                while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+                const int j = i + 1 + rem;
+                rx = x[2 * i] - x[2 * j]; ry = x[2 * i + 1] - x[2 * j + 1];
+            } else { const int i = it_p - NP; rx = x[2 * i]; ry = x[2 * i + 1]; }
+            const double d = sqrt(fma(rx, rx, ry * ry));
+            double f[4];
+            if (pair) radial_mlp<1>(coef_eta, a.H_eta, d, tab, f);
+            else radial_mlp<1>(coef_mu, a.H_mu, d, tab, f);
+            G[0] = f[0] * rx; G[1] = f[0] * ry;
+            G[2] = (pair ? 2.0 : 1.0) * fma(f[1], d, 2.0 * f[0]);
+        }
+        __syncthreads();
+        for (int g = tid; g < W * D; g += T) {
+            int w = g / D, e = g - w * D, i = e >> 1, c = e & 1;
+            long long b = base + w;
+            const double* G = wb + (size_t)w * wstride + D;
+            double acc = 0.0;
+            for (int j = 0; j < i; ++j) acc -= G[3 * pair_index(j, i, n) + c];
+            for (int j = i + 1; j < n; ++j) acc += G[3 * pair_index(i, j, n) + c];
+            if (has_mu) acc += G[3 * (NP + i) + c];
+            if (b < a.B && a.v) a.v[b * D + e] = acc;
+        }
+        for (int w = tid; w < W; w += T) {
+            long long b = base + w;
+            const double* G = wb + (size_t)w * wstride + D;
+            double acc = 0.0;
+            for (int p = 0; p < P; ++p) acc += G[3 * p + 2];
+            if (b < a.B && a.div) a.div[b] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// log|det|, gradient and Laplacian of one or two spin blocks (slater.py, base_dist.py:48).
+// scale = 1 for LogAbsSlaterDet, 2 for FreeFermion.log_prob.
+// ---------------------------------------------------------------------------------------
+struct SlaterArgs {
+    int n, n_up;
+    long long B;
+    const double* x;
+    const int* orb;
+    const int* walker_state;
+    double scale;
+    double *logabs, *grad, *lap;
+    int W, wstride;       // doubles per walker: D + scratch + n*n
+};
+
+__global__ void __launch_bounds__(256) slater_kernel(const SlaterArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int n = a.n, D = 2 * n, W = a.W;
+    const int slsz = slater_scratch_size(a.n_up, n - a.n_up);
+    auto xw = [&](int w) { return smem + (size_t)w * a.wstride; };
+    auto scr = [&](int w) { return xw(w) + D; };
+    auto red = [&](int w) { return xw(w) + D + slsz; };
+    const bool deriv = a.grad != nullptr || a.lap != nullptr;
+    for (long long base = (long long)blockIdx.x * W; base < a.B; base += (long long)gridDim.x * W) {
+        __syncthreads();
+        for (int g = tid; g < W * D; g += T) {
+            int w = g / D, e = g - w * D;
+            long long b = base + w;
+            xw(w)[e] = (b < a.B) ? a.x[b * D + e] : (double)(e >> 1) + 0.37 * (e & 1);
+        }
+        __syncthreads();
+        auto orbp = [&](int w) { long long b = base + w; int row = (a.walker_state && b < a.B) ? a.walker_state[b] : 0;
+                                 return a.orb + (size_t)row * n; };
+        if (deriv) slater_team<true>(W, n, a.n_up, [&](int w) { return (const double*)xw(w); }, scr, orbp);
+        else slater_team<false>(W, n, a.n_up, [&](int w) { return (const double*)xw(w); }, scr, orbp);
+        if (deriv) {
+            for (int g = tid; g < W * n * n; g += T) {
+                int w = g / (n * n), rem = g - w * n * n;
+                int I = rem / n, J = rem - I * n;
+                const int sI = I >= a.n_up, sJ = J >= a.n_up;
+                double t = 0.0;
+                if (sI == sJ) {
+                    const SlBlk blk = slater_blk(sI, n, a.n_up);
+                    const int ns = blk.ns, i = I - blk.i0, j = J - blk.i0;
+                    const double* S = scr(w);
+                    if (i == j) {      // Laplacian = trace of H: C^{xx}_i + C^{yy}_i - (B^x_ii)^2 - (B^y_ii)^2
+                        const double gx = S[blk.bx() + i * ns + i], gy = S[blk.by() + i * ns + i];
+                        t = S[blk.cc() + 3 * i] + S[blk.cc() + 3 * i + 2] - gx * gx - gy * gy;
+                        long long b = base + w;
+                        if (b < a.B && a.grad) {
+                            a.grad[b * D + 2 * I] = a.scale * S[blk.bx() + i * ns + i];
+                            a.grad[b * D + 2 * I + 1] = a.scale * S[blk.by() + i * ns + i];
+                        }
+                    }
+                }
+                red(w)[rem] = t;
+            }
+            __syncthreads();
+        }
+        for (int w = tid; w < W; w += T) {
+            long long b = base + w;
+            if (b >= a.B) continue;
+            const double* S = scr(w);
+            const SlBlk bu = slater_blk(0, n, a.n_up), bd = slater_blk(1, n, a.n_up);
+            double ld = 0.0;
+            if (bu.ns) ld += S[bu.misc() + 2];
+            if (bd.ns) ld += S[bd.misc() + 2];
+            if (a.logabs) a.logabs[b] = a.scale * ld;
+            if (a.lap) {
+                double acc = 0.0;
+                for (int k = 0; k < n * n; ++k) acc += red(w)[k];
+                a.lap[b] = a.scale * acc;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Metropolis sampling of |Psi_0|^2 (base_dist.py:58-70, 103-134), one thread per walker.
+// Per-thread matrices live in shared memory, element e of thread t at sm[e * T + t].
+// ---------------------------------------------------------------------------------------
+struct MetroArgs {
+    long long B;
+    int n, n_up;
+    const int* orb;
+    const int* walker_state;
+    int steps;
+    double tau;
+    unsigned long long seed;
+    long long walker_offset;
+    const double *x0, *normals, *uniforms;     // parity mode when non-null
+    double* x;
+    int* accept_count;
+    double* gscratch;       // global fallback for the matrices when shared memory is too small
+    int use_global;
+};
+
+// log|det Phi| of one spin block via LU with partial pivoting; X points at the coordinates
+// (interleaved with stride T), A is the ns x ns work matrix (interleaved with stride sa).
+__device__ __forceinline__ double metro_logdet(const double* X, int xs, int i0, int ns, const int* orb,
+                                               double* A, size_t sa) {
+    const double inv_sqrt_pi = 0.56418958354775628695;
+    for (int r = 0; r < ns; ++r) {
+        Herm1D hx, hy;
+        hermite_1d(X[(size_t)(2 * (i0 + r)) * xs], 7, hx);
+        hermite_1d(X[(size_t)(2 * (i0 + r) + 1) * xs], 7, hy);
+        for (int c = 0; c < ns; ++c) {
+            const int id = orb[i0 + c];
+            const int nx = c_orb_nx[id], ny = c_orb_ny[id];
+            double vx = 0, vy = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { if (q == nx) vx = hx.v[q]; if (q == ny) vy = hy.v[q]; }
+            A[(size_t)(r * ns + c) * sa] = inv_sqrt_pi * vx * vy;
+        }
+    }
+    double ld = 0.0;
+    for (int k = 0; k < ns; ++k) {
+        int p = k; double best = fabs(A[(size_t)(k * ns + k) * sa]);
+        for (int r = k + 1; r < ns; ++r) {
+            const double v = fabs(A[(size_t)(r * ns + k) * sa]);
+            if (v > best) { best = v; p = r; }
+        }
+        if (p != k) {
+            for (int c = k; c < ns; ++c) {
+                const double t = A[(size_t)(k * ns + c) * sa];
+                A[(size_t)(k * ns + c) * sa] = A[(size_t)(p * ns + c) * sa];
+                A[(size_t)(p * ns + c) * sa] = t;
+            }
+        }
+        ld += log(best);
+        const double ipv = 1.0 / A[(size_t)(k * ns + k) * sa];
+        for (int r = k + 1; r < ns; ++r) {
+            const double l = A[(size_t)(r * ns + k) * sa] * ipv;
+            for (int c = k + 1; c < ns; ++c)
+                A[(size_t)(r * ns + c) * sa] = fma(-l, A[(size_t)(k * ns + c) * sa], A[(size_t)(r * ns + c) * sa]);
+        }
+    }
+    return ld;
+}
+
+__global__ void __launch_bounds__(128) metropolis_kernel(const MetroArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, T = blockDim.x;
+    const long long b = (long long)blockIdx.x * T + tid;
+    const int n = a.n, D = 2 * n, n_up = a.n_up, n_dn = n - n_up;
+    const int nsm = max(n_up, n_dn);
+    double* X = smem + tid;                        // current, D entries, stride T
+    double* Y = smem + (size_t)D * T + tid;        // proposal
+    double* A; size_t sa;
+    if (a.use_global) { A = a.gscratch + b; sa = (size_t)gridDim.x * T; }
+    else { A = smem + (size_t)2 * D * T + tid; sa = T; }
+    (void)nsm;
+    if (b >= a.B) return;
+    const int* orb = a.orb + (size_t)((a.walker_state ? a.walker_state[b] : 0)) * n;
+    const unsigned long long wid = (unsigned long long)(b + a.walker_offset);
+    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    auto normal_pair = [&](uint32_t step, uint32_t slot, double& g0, double& g1) {
+        uint4 r = philox4x32_10(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), step, slot), key);
+        const double u1 = u01_53(r.x, r.y), u2 = u01_53(r.z, r.w);
+        const double rad = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        g0 = rad * cs; g1 = rad * sn;
+    };
+    for (int i = 0; i < n; ++i) {
+        double g0, g1;
+        if (a.x0) { g0 = a.x0[b * D + 2 * i]; g1 = a.x0[b * D + 2 * i + 1]; }
+        else normal_pair(0u, (uint32_t)i, g0, g1);
+        X[(size_t)(2 * i) * T] = g0; X[(size_t)(2 * i + 1) * T] = g1;
+    }
+    double logp = 2.0 * ((n_up ? metro_logdet(X, T, 0, n_up, orb, A, sa) : 0.0) +
+                         (n_dn ? metro_logdet(X, T, n_up, n_dn, orb, A, sa) : 0.0));
+    int acc = 0;
+    for (int s = 0; s < a.steps; ++s) {
+        for (int i = 0; i < n; ++i) {
+            double g0, g1;
+            if (a.normals) {
+                const double* e = a.normals + ((size_t)s * a.B + b) * D + 2 * i;
+                g0 = e[0]; g1 = e[1];
+            } else normal_pair((uint32_t)(s + 1), (uint32_t)i, g0, g1);
+            Y[(size_t)(2 * i) * T] = fma(a.tau, g0, X[(size_t)(2 * i) * T]);
+            Y[(size_t)(2 * i + 1) * T] = fma(a.tau, g1, X[(size_t)(2 * i + 1) * T]);
+        }
+        const double nlogp = 2.0 * ((n_up ? metro_logdet(Y, T, 0, n_up, orb, A, sa) : 0.0) +
+                                    (n_dn ? metro_logdet(Y, T, n_up, n_dn, orb, A, sa) : 0.0));
+        double u;
+        if (a.uniforms) u = a.uniforms[(size_t)s * a.B + b];
+        else {
+            uint4 r = philox4x32_10(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)(s + 1), 0xFFFFFFFFu), key);
+            u = u01_53(r.x, r.y);
+        }
+        if (u < exp(nlogp - logp)) {
+            for (int e = 0; e < D; ++e) X[(size_t)e * T] = Y[(size_t)e * T];
+            logp = nlogp;
+            ++acc;
+        }
+    }
+    for (int e = 0; e < D; ++e) a.x[b * D + e] = X[(size_t)e * T];
+    if (a.accept_count) a.accept_count[b] = acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// potentials.py: 1/2 sum r^2 and Z sum_{i<j} 1/r_ij, one thread per walker.
+// ---------------------------------------------------------------------------------------
+__global__ void potential_kernel(const double* x, long long B, int n, double Z, int harmonic, double* V) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double* p = x + b * 2 * n;
+    double vh = 0.0, vc = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double xi = p[2 * i], yi = p[2 * i + 1];
+        vh = fma(xi, xi, fma(yi, yi, vh));
+        for (int j = i + 1; j < n; ++j) {
+            const double dx = xi - p[2 * j], dy = yi - p[2 * j + 1];
+            vc += 1.0 / sqrt(fma(dx, dx, dy * dy));
+        }
+    }
+    V[b] = Z * vc + (harmonic ? 0.5 * vh : 0.0);
+}
+
+// ---------------------------------------------------------------------------------------
+// Boltzmann / categorical occupation sampling (VMC.py:94-97) by inverse CDF.
+// ---------------------------------------------------------------------------------------
+__global__ void occupation_cdf_kernel(const double* logits, int S, double* cdf, int* counts) {
+    // single thread: S is the number of many-body states (tens to a few thousand); the
+    // sequential sum is the definition the oracle mirrors (softmax -> cumsum -> normalise).
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double mx = logits[0];
+        for (int s = 1; s < S; ++s) mx = fmax(mx, logits[s]);
+        double tot = 0.0;
+        for (int s = 0; s < S; ++s) tot += exp(logits[s] - mx);
+        double run = 0.0;
+        for (int s = 0; s < S; ++s) { run += exp(logits[s] - mx) / tot; cdf[s] = run; }
+        const double last = cdf[S - 1];
+        for (int s = 0; s < S; ++s) cdf[s] /= last;
+    }
+    for (int s = threadIdx.x; s < S; s += blockDim.x) counts[s] = 0;
+}
+__global__ void occupation_search_kernel(const double* cdf, int S, const double* u, long long B, int* counts) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double ub = u[b];
+    int lo = 0, hi = S;              // first index with cdf[idx] >= u  (torch.searchsorted, right=False)
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf[mid] < ub) lo = mid + 1; else hi = mid; }
+    if (lo > S - 1) lo = S - 1;
+    atomicAdd(&counts[lo], 1);
+}
+// sorted state list: walker b gets the state s with prefix[s] <= b < prefix[s+1]
+__global__ void occupation_fill_kernel(const int* counts, int S, long long B, int* state) {
+    __shared__ long long start;
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        if (threadIdx.x == 0) { long long acc = 0; for (int q = 0; q < s; ++q) acc += counts[q]; start = acc; }
+        __syncthreads();
+        const long long st = start; const int c = counts[s];
+        for (int k = threadIdx.x; k < c; k += blockDim.x) if (st + k < B) state[st + k] = s;
+        __syncthreads();
+    }
+}
+
 // Dependent-chain DFMA throughput probe: 8 independent chains per thread.
 __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, double* sink) {
     double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
@@ -15,4 +356,5 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, 
     double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 123.456) sink[0] = s;
 }
+
 }  // namespace ff

@@ -1,0 +1,106 @@
+"""Continuous normalizing flow of fermion coordinates -- mirror of reference src/flow.py
+(CNF) and src/NeuralODE/nnModule.py (solve_ivp_nnmodule + adjoint), on fixed-step 3/8-rule
+RK4 CUDA kernels (C ABI ff_cnf_generate / ff_cnf_delta_logp / ff_eloc / ff_logp_backward).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _flat_params(v):
+    ps = list(v.eta.parameters_in_kernel_order())
+    if v.mu is not None:
+        ps += list(v.mu.parameters_in_kernel_order())
+    return ps
+
+
+class _Stash:
+    """Device buffers the backward sweep needs (what ctx.save_for_backward holds in
+    nnModule.py:73)."""
+
+    def __init__(self, model, B, device):
+        ny, nc, nw = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        L.check(L.lib().ff_stash_sizes(C.byref(model), B, C.byref(ny), C.byref(nc)))
+        L.check(L.lib().ff_backward_work_size(C.byref(model), B, C.byref(nw)))
+        self.y = torch.empty(ny.value, dtype=torch.float64, device=device)
+        self.c = torch.empty(nc.value, dtype=torch.float64, device=device)
+        self.n_work = nw.value
+
+
+def _backward_through_flow(cnf, model, stash, B, gbar_z, gbar_delta, need_x):
+    """ff_logp_backward: returns grad_x (or None) and the list of parameter gradients."""
+    dev = gbar_z.device
+    v = cnf.v
+    params = _flat_params(v)
+    grads = [torch.zeros(p.numel(), dtype=torch.float64, device=dev) for p in params]
+    gp = [L.ptr(g) for g in grads] + [None] * (6 - len(grads))
+    grad_x = torch.empty_like(gbar_z) if need_x else None
+    work = torch.empty(stash.n_work, dtype=torch.float64, device=dev)
+    L.check(L.lib().ff_logp_backward(C.byref(model), B, L.ptr(stash.y), L.ptr(stash.c),
+                                     L.ptr(gbar_z.contiguous()), L.ptr(gbar_delta.contiguous()),
+                                     L.ptr(grad_x), *gp, L.ptr(work), L.stream()))
+    return grad_x, [g.view_as(p) for g, p in zip(grads, params)]
+
+
+class _DeltaLogp(torch.autograd.Function):
+    """(z, delta_logp) = flow^{-1}(x) with a hand-written backward (nnModule.py:8-103)."""
+
+    @staticmethod
+    def forward(ctx, cnf, x, with_params, *params):
+        x = x.detach().contiguous()
+        B, n, _ = x.shape
+        model = cnf._model(n)
+        z = torch.empty_like(x)
+        dl = torch.empty(B, dtype=x.dtype, device=x.device)
+        need_bwd = any(ctx.needs_input_grad)
+        stash = _Stash(model, B, x.device) if need_bwd else None
+        L.check(L.lib().ff_cnf_delta_logp(C.byref(model), L.ptr(x), B, L.ptr(z), L.ptr(dl),
+                                          L.ptr(stash.y) if stash else None,
+                                          L.ptr(stash.c) if stash else None, L.stream()))
+        ctx.cnf, ctx.model, ctx.stash, ctx.B = cnf, model, stash, B
+        ctx.n_params = len(params)
+        return z, dl
+
+    @staticmethod
+    def backward(ctx, gz, gdl):
+        B = ctx.B
+        dev = ctx.stash.y.device
+        gz = torch.zeros(B, ctx.model.n_up + ctx.model.n_dn, 2, dtype=torch.float64, device=dev) if gz is None else gz
+        gdl = torch.zeros(B, dtype=torch.float64, device=dev) if gdl is None else gdl
+        gx, gparams = _backward_through_flow(ctx.cnf, ctx.model, ctx.stash, B, gz, gdl, ctx.needs_input_grad[1])
+        if ctx.n_params == 0:
+            gparams = []
+        return (None, gx, None, *gparams)
+
+
+class CNF(torch.nn.Module):
+    """CNF(v, t_span, nsteps): v is a Backflow; nsteps RK4 steps across t_span
+    (the reference's adaptive dopri5 with rtol 1e-6 is replaced by a fixed grid)."""
+
+    def __init__(self, v, t_span, nsteps=16):
+        super().__init__()
+        self.v = v
+        self.t_span = (float(t_span[0]), float(t_span[1]))
+        self.nsteps = int(nsteps)
+
+    def _model(self, n, n_up=None):
+        return self.v._model(n, self.t_span, self.nsteps, n_up=n_up)
+
+    def generate(self, z, nframes=None):               # flow.py:42-50
+        if nframes is not None:
+            raise NotImplementedError("trajectory frames (nframes) are visualisation only and not on the CUDA path")
+        z = z.detach().contiguous()
+        B, n, _ = z.shape
+        m = self._model(n)
+        x = torch.empty_like(z)
+        L.check(L.lib().ff_cnf_generate(C.byref(m), L.ptr(z), B, 0, L.ptr(x), L.stream()))
+        return x
+
+    def delta_logp(self, x, params_require_grad=False):  # flow.py:52-56
+        params = _flat_params(self.v) if params_require_grad else []
+        return _DeltaLogp.apply(self, x, params_require_grad, *params)
+
+    def backflow_potential(self):                        # flow.py:86-92
+        return self.v.eta, self.v.mu

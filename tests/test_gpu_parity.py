@@ -1,0 +1,341 @@
+"""GPU parity tests: the CUDA path (through the Python mirror -> C ABI) against the CPU
+oracle and the golden vectors produced by the real reference.  Tolerances: 1e-10 relative
+(BASELINE.json north_star) unless a looser, documented bound applies."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+torch.set_default_dtype(torch.float64)
+T = torch.from_numpy
+RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import fermiflow_oracle
+    return fermiflow_oracle
+
+
+def close(a, b, rtol=RTOL, atol=0.0):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = np.abs(a - b).max() if a.size else 0.0
+    assert err <= atol + rtol * (np.abs(b).max() if b.size else 0.0), (err, np.abs(b).max())
+
+
+def mlp_from(g, name, dev):
+    from fermiflow_b200 import MLP
+    H = len(g[name + "_w1"])
+    m = MLP(1, H)
+    with torch.no_grad():
+        m.fc1.weight.copy_(T(g[name + "_w1"])[:, None])
+        m.fc1.bias.copy_(T(g[name + "_b1"]))
+        m.fc2.weight.copy_(T(g[name + "_w2"])[None])
+    return m.to(dev)
+
+
+def rand_mlp(H, seed, scale, dev):
+    from fermiflow_b200 import MLP
+    gen = torch.Generator().manual_seed(seed)
+    m = MLP(1, H)
+    with torch.no_grad():
+        m.fc1.weight.copy_(torch.randn(H, 1, generator=gen))
+        m.fc1.bias.copy_(torch.randn(H, generator=gen))
+        m.fc2.weight.copy_(scale * torch.randn(1, H, generator=gen))
+    return m.to(dev)
+
+
+def cpu_params(m):
+    return tuple(t.cpu() for t in m.kernel_params())
+
+
+# ---------------------------------------------------------------------------------------
+def test_backflow_vs_reference(dev, golden):
+    from fermiflow_b200 import Backflow
+    g = golden("backflow")
+    eta, mu = mlp_from(g, "eta", dev), mlp_from(g, "mu", dev)
+    x = T(g["x"]).to(dev)
+    v = Backflow(eta, mu=mu)
+    close(v(x), g["v"])
+    close(v.divergence(x), g["div"])
+    v2 = Backflow(eta)
+    close(v2(x), g["v_nomu"])
+    close(v2.divergence(x), g["div_nomu"])
+
+
+def test_backflow_equivariance(dev):
+    """reference tests/test_equivariant_funs.py:4 at the N=20 size."""
+    from fermiflow_b200 import Backflow
+    v = Backflow(rand_mlp(50, 3, 0.1, dev), mu=rand_mlp(50, 4, 0.1, dev))
+    x = torch.randn(1000, 20, 2, device=dev)
+    P = torch.randperm(20, device=dev)
+    close(v(x[:, P]), v(x)[:, P], 1e-12)
+    close(v.divergence(x[:, P]), v.divergence(x), 1e-12)
+
+
+def test_slater_vs_reference(dev, golden):
+    from fermiflow_b200 import HO2D
+    from fermiflow_b200.slater import LogAbsSlaterDet, slater_value_grad_laplacian
+    ho, g = HO2D(), golden("slater")
+    for name in ("gs6", "gs10", "rand7"):
+        orbs = tuple(ho.orbitals[k] for k in g[name + "_idx"])
+        x = T(g[name + "_x"]).to(dev)
+        y, gr, lap = slater_value_grad_laplacian(orbs, x)
+        close(y, g[name + "_logabsdet"])
+        close(gr, g[name + "_grad"])
+        close(lap, g[name + "_lap"], 1e-9)
+        xr = x.clone().requires_grad_(True)
+        out = LogAbsSlaterDet.apply(orbs, xr)
+        (out * torch.arange(1, len(out) + 1, device=dev)).sum().backward()
+        close(xr.grad, g[name + "_grad"] * np.arange(1, len(out) + 1)[:, None, None])
+
+
+def test_free_fermion_logp_vs_reference(dev, golden):
+    from fermiflow_b200 import HO2D, FreeFermion
+    ho, g = HO2D(), golden("slater")
+    x = T(g["ff_x"]).to(dev).requires_grad_(True)
+    lp = FreeFermion(dev).log_prob(ho.orbitals[:3], ho.orbitals[:2], x)
+    close(lp, g["ff_logp"])
+    lp.sum().backward()
+    close(x.grad, g["ff_grad"])
+
+
+def test_multistates_vs_reference(dev, golden):
+    from fermiflow_b200 import HO2D, FreeFermion
+    from fermiflow_b200.slater import LogAbsSlaterDetMultStates
+    ho, g = HO2D(), golden("states")
+    for nup, dE in ((3, 2), (6, 2), (3, 4), (10, 2), (4, 3)):
+        states, Es = ho.fermion_states(nup, 0, dE)
+        idx = np.array([[o.index for o in up] for up, _ in states])
+        assert np.array_equal(idx, g["states_%d_%d" % (nup, dE)])
+        assert np.array_equal(np.array(Es), g["Es_%d_%d" % (nup, dE)])
+    states, _ = ho.fermion_states(3, 0, 2)
+    ws = T(g["ms_state_idx"]).to(dev).to(torch.int32)
+    x = T(g["ms_x"]).to(dev).requires_grad_(True)
+    out = LogAbsSlaterDetMultStates.apply(tuple(up for up, _ in states), ws, x)
+    close(out, g["ms_logabsdet"])
+    out.sum().backward()
+    close(x.grad, g["ms_grad"])
+    lp = FreeFermion(dev).log_prob_multstates(states, ws, x.detach())
+    close(lp, 2 * g["ms_logabsdet"])
+
+
+def test_potentials_vs_reference(dev, golden):
+    from fermiflow_b200 import HO, CoulombPairPotential
+    g = golden("potentials")
+    x = T(g["x"]).to(dev)
+    close(HO().V(x), g["ho"], 1e-13)
+    close(CoulombPairPotential(float(g["Z"])).V(x), g["coulomb"], 1e-13)
+
+
+def _golden_model(g, dev, nsteps):
+    from fermiflow_b200 import Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
+    eta, mu = mlp_from(g, "eta", dev), mlp_from(g, "mu", dev)
+    cnf = CNF(Backflow(eta, mu=mu), tuple(g["t_span"]), nsteps=nsteps)
+    model = GSVMC(int(g["nup"]), int(g["ndown"]), HO2D(), FreeFermion(dev), cnf,
+                  CoulombPairPotential(float(g["Z"])), sp_potential=HO())
+    return model.to(dev), eta, mu
+
+
+def test_cnf_vs_reference_same_solver(dev, golden):
+    """Reference run with odeint(method='rk4', 16 steps): identical discrete algorithm."""
+    g = golden("pipeline")
+    model, _, _ = _golden_model(g, dev, 16)
+    x = model.cnf.generate(T(g["z0"]).to(dev))
+    close(x, g["rk4s16_x"], 1e-12)
+    z, dl = model.cnf.delta_logp(T(g["rk4s16_x"]).to(dev))
+    close(z, g["rk4s16_zback"], 1e-12)
+    close(dl, g["rk4s16_delta_logp"], 1e-11, 1e-14)
+    close(model.logp(T(g["rk4s16_x"]).to(dev)), g["rk4s16_logp"], 1e-12)
+
+
+def test_eloc_vs_tight_reference(dev, golden):
+    """Reference adaptive solver at rtol 1e-11 (adjoint gradient, nested-adjoint Laplacian)
+    against the 64-step CUDA sweep: same continuous quantities; the bound is the
+    reference's own integration error."""
+    g = golden("pipeline")
+    model, eta, mu = _golden_model(g, dev, 64)
+    x = T(g["tight_x"]).to(dev)
+    r = model.local_energy(x, stash=True)
+    close(r.logp, g["tight_logp"], 1e-10)
+    close(r.grad, g["tight_grad"], 1e-8)
+    close(r.lap, g["tight_lap"], 1e-7)
+    close(r.eloc, g["tight_eloc"], 1e-7)
+    lp = model.logp(x, params_require_grad=True)
+    (lp * T(g["weights"]).to(dev)).sum().backward()
+    for p, k in ((eta.fc1.weight, "eta_w1"), (eta.fc1.bias, "eta_b1"), (eta.fc2.weight, "eta_w2"),
+                 (mu.fc1.weight, "mu_w1"), (mu.fc1.bias, "mu_b1"), (mu.fc2.weight, "mu_w2")):
+        close(p.grad.reshape(-1), g["tight_g_" + k], 1e-8, 1e-12)
+
+
+CASES = [  # nup, ndown, H_eta, H_mu, nsteps, batch
+    (3, 2, 8, 6, 16, 5),
+    (3, 0, 8, 0, 8, 7),
+    (1, 1, 5, 5, 4, 3),
+    (6, 6, 16, 16, 8, 9),
+    (5, 2, 50, 50, 4, 4),
+]
+
+
+@pytest.mark.parametrize("nup,ndn,H,Hm,S,B", CASES)
+def test_eloc_and_gradients_vs_oracle(dev, O, nup, ndn, H, Hm, S, B):
+    from fermiflow_b200 import Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
+    from fermiflow_b200.VMC import _LogpFromSweep
+    from fermiflow_b200.flow import _flat_params
+    n = nup + ndn
+    eta = rand_mlp(H, 1, 0.05, dev)
+    mu = rand_mlp(Hm, 2, 0.05, dev) if Hm else None
+    ts = (0.0, 1.0)
+    cnf = CNF(Backflow(eta, mu=mu), ts, nsteps=S)
+    model = GSVMC(nup, ndn, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(2.0), sp_potential=HO()).to(dev)
+    gen = torch.Generator().manual_seed(5)
+    z0 = 0.9 * torch.randn(B, n, 2, generator=gen)
+    w = torch.randn(B, generator=gen) / B
+    eta_c, mu_c = cpu_params(eta), (cpu_params(mu) if mu is not None else None)
+    up, dn = list(range(nup)), list(range(ndn))
+
+    x = cnf.generate(z0.to(dev))
+    x_ref = O.cnf_generate(z0, eta_c, mu_c, ts, S)
+    close(x, x_ref, 1e-12)
+    r = model.local_energy(x, stash=True)
+    ref = O.local_energy(x_ref, up, dn, eta_c, mu_c, ts, S, 2.0)
+    close(r.logp, ref["logp"])
+    close(r.grad, ref["grad"])
+    close(r.lap, ref["lap"])
+    close(r.kinetic, ref["kinetic"])
+    close(r.potential, ref["potential"])
+    close(r.eloc, ref["eloc"])
+
+    gref = O.weighted_logp_param_grad(x_ref, w, up, dn, eta_c, mu_c, ts, S)
+    names = [eta.fc1.weight, eta.fc1.bias, eta.fc2.weight] + ([mu.fc1.weight, mu.fc1.bias, mu.fc2.weight] if mu else [])
+    # (a) through the fused sweep, as GSVMC.forward does
+    lp = _LogpFromSweep.apply(model, r, model._orb(dev), None, nup, ndn, *_flat_params(cnf.v))
+    (lp * w.to(dev)).sum().backward()
+    for p, gr in zip(names, gref):
+        close(p.grad.reshape(-1), gr.reshape(-1), 1e-9, 1e-13)
+        p.grad = None
+    # (b) through the reference-shaped API: logp(x, params_require_grad=True)
+    xr = x.clone().requires_grad_(True)
+    lp = model.logp(xr, params_require_grad=True)
+    close(lp, ref["logp"])
+    (lp * w.to(dev)).sum().backward()
+    for p, gr in zip(names, gref):
+        close(p.grad.reshape(-1), gr.reshape(-1), 1e-9, 1e-13)
+    # the adjoint's d/dx must equal the forward-mode gradient
+    close(xr.grad, ref["grad"] * w[:, None, None], 1e-9, 1e-13)
+
+
+def test_noninteracting_eigenstates_full_size(dev):
+    """Known answer (reference tests/test_basedist.py:5): with a zero flow and Z = 0 every
+    walker's E_loc is the sum of the occupied HO levels -- N = 20 (10 up / 10 down), 4096
+    walkers drawn by the Metropolis kernel, E = 2 * (1 + 2*2 + 3*3 + 4*4) = 60."""
+    from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
+    eta, mu = MLP(1, 50), MLP(1, 50)
+    eta.init_zeros(); mu.init_zeros()
+    cnf = CNF(Backflow(eta, mu=mu), (0.0, 1.0), nsteps=4)
+    model = GSVMC(10, 10, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(0.0), sp_potential=HO()).to(dev)
+    z, x = model.sample((4096,))
+    close(x, z, 1e-15)
+    r = model.local_energy(x)
+    close(r.eloc, torch.full((4096,), 60.0), 1e-9)
+
+
+def test_multistate_eigenstates(dev):
+    """reference tests/test_basedist.py:58: each excited determinant is an eigenfunction."""
+    from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, BetaVMC, HO, CoulombPairPotential
+    eta = MLP(1, 8); eta.init_zeros()
+    cnf = CNF(Backflow(eta), (0.0, 1.0), nsteps=2)
+    model = BetaVMC(2.0, 4, 0, 3, True, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(0.0), sp_potential=HO()).to(dev)
+    gF_phi, gF_theta = model(2048)
+    Es = model.Es_original.to(dev)[model.state_indices.long()]
+    close(model.last.eloc, Es, 1e-9)
+    assert sum(model.state_indices_collection.values()) == 2048
+    gF_phi.backward(); gF_theta.backward()
+    assert torch.isfinite(model.log_state_weights.grad).all()
+    assert abs(model.S - model.S_analytical) < 0.2
+
+
+def test_metropolis_replay_vs_oracle(dev, O):
+    from fermiflow_b200 import HO2D, FreeFermion
+    ho = HO2D()
+    gen = torch.Generator().manual_seed(11)
+    B, nup, ndn, steps = 64, 3, 2, 25
+    x0 = torch.randn(B, nup + ndn, 2, generator=gen)
+    nrm = torch.randn(steps, B, nup + ndn, 2, generator=gen)
+    uni = torch.rand(steps, B, generator=gen)
+    ref = O.metropolis_sample(list(range(nup)), list(range(ndn)), x0, nrm, uni, tau=0.1)
+    x = FreeFermion(dev).sample(ho.orbitals[:nup], ho.orbitals[:ndn], (B,), equilibrim_steps=steps,
+                                noise=(x0.to(dev), nrm.to(dev), uni.to(dev)))
+    close(x, ref, 1e-13)
+
+
+def test_metropolis_philox_stream(dev, O):
+    """steps = 0 returns the initial normals: Philox4x32-10 counters (walker, 0, step 0,
+    particle) -> Box-Muller, reproduced in numpy."""
+    from fermiflow_b200 import HO2D, FreeFermion
+    ho = HO2D()
+    fd = FreeFermion(dev); fd.manual_seed(1234)
+    B, n = 33, 4
+    x = fd.sample(ho.orbitals[:n], (), (B,), equilibrim_steps=0).cpu().numpy()
+    ctr = np.zeros((B, n, 4), np.uint32)
+    ctr[..., 0] = np.arange(B)[:, None]
+    ctr[..., 3] = np.arange(n)[None, :]
+    key = np.zeros((B, n, 2), np.uint32); key[..., 0] = 1234
+    r = O.philox4x32_10(ctr, key)
+    u1, u2 = O.u01_from_bits(r[..., 0], r[..., 1]), O.u01_from_bits(r[..., 2], r[..., 3])
+    rad = np.sqrt(-2 * np.log(u1))
+    ref = np.stack([rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)], -1)
+    assert np.abs(x - ref).max() < 1e-13
+
+
+def test_occupation_sampling_bit_exact(dev, O):
+    from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, BetaVMC, HO, CoulombPairPotential
+    eta = MLP(1, 4)
+    cnf = CNF(Backflow(eta), (0.0, 1.0), nsteps=2)
+    model = BetaVMC(10.0, 3, 0, 2.0, True, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(2.0), sp_potential=HO()).to(dev)
+    u = torch.rand(100000, generator=torch.Generator().manual_seed(3))
+    state = model.sample_states(100000, uniforms=u.to(dev))
+    ref = O.categorical_from_uniforms(O.boltzmann_logits(10.0, model.Es_original), u)
+    assert torch.equal(state.cpu().long(), ref)
+    model2 = BetaVMC(0.7, 6, 0, 2.0, True, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(2.0), sp_potential=HO()).to(dev)
+    state = model2.sample_states(100000, uniforms=u.to(dev))
+    ref = O.categorical_from_uniforms(O.boltzmann_logits(0.7, model2.Es_original), u)
+    assert torch.equal(state.cpu().long(), ref)
+
+
+def test_edge_cases(dev):
+    from fermiflow_b200 import Backflow, CNF
+    cnf = CNF(Backflow(rand_mlp(8, 1, 0.1, dev), mu=rand_mlp(8, 2, 0.1, dev)), (0.0, 1.0), nsteps=3)
+    x = cnf.generate(torch.empty(0, 4, 2, device=dev))
+    assert x.shape == (0, 4, 2)
+    one = cnf.generate(torch.randn(1, 1, 2, device=dev))          # a single particle, mu only
+    assert torch.isfinite(one).all()
+    with pytest.raises(RuntimeError):
+        cnf.generate(torch.randn(2, 4, 2))                          # CPU tensor: no fallback
+    # ragged batch (not a multiple of the walkers-per-CTA) and round trip x -> z -> x
+    z = torch.randn(1001, 6, 2, device=dev)
+    x = cnf.generate(z)
+    zb, _ = cnf.delta_logp(x)
+    assert (zb - z).abs().max() < 1e-2          # 3 RK4 steps only: truncation error
+
+
+def test_flow_reversibility_full_size(dev):
+    """flow.py:58-71 check_reversibility at N = 20: z -> x -> z within the RK4 error."""
+    from fermiflow_b200 import Backflow, CNF
+    cnf = CNF(Backflow(rand_mlp(50, 7, 0.02, dev), mu=rand_mlp(50, 8, 0.02, dev)), (0.0, 1.0), nsteps=32)
+    z = torch.randn(4096, 20, 2, device=dev)
+    x = cnf.generate(z)
+    zb, dl = cnf.delta_logp(x)
+    assert (zb - z).abs().max() < 1e-4          # RK4 truncation error (close pairs: |r| cone)
+    assert (zb - z).abs().mean() < 1e-7
+    assert torch.isfinite(dl).all()
