@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- VMC walker-updates/s (sample + E_loc + grad) on the N = 20 ground-state quantum dot.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" is one VMC iteration of reference src/FermionHO2D.py's loop body on `--walkers`
+walkers per GPU: Metropolis sampling of the base state, flow z -> x, local energy (log p,
+its gradient and Laplacian), energy gradient w.r.t. the flow parameters, all-reduce of the
+energy moments and the gradient, Adam update.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+torch.set_default_dtype(torch.float64)
+
+METRIC = "VMC walker-updates/s (sample+E_loc+grad) N=20"
+UNIT = "walker-updates/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--walkers", type=int, default=65536, help="walkers per GPU")
+    p.add_argument("--nup", type=int, default=10)
+    p.add_argument("--ndown", type=int, default=10)
+    p.add_argument("--hidden", type=int, default=50, help="Deta = Dmu (reference default 50)")
+    p.add_argument("--Z", type=float, default=2.0)
+    p.add_argument("--ode-steps", type=int, default=16, help="RK4 steps across t_span")
+    p.add_argument("--ref-walkers", type=int, default=4, help="walkers per step of the CPU reference arm")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mhz = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons}
+
+
+def flops_per_walker_eloc(n, H_eta, H_mu, ode_steps):
+    """Algorithmic FP64 flop count of one E_loc sweep per walker (kernel K_eloc):
+    per RK stage, items x hidden x 43 flop (sigmoid 25, pre-activation 2, three derivative
+    factors 8, four accumulations 8) + Jacobian GEMM 2 D^3 + Gram matrix 4 n (n+1) D / 2 * 2."""
+    D, NP = 2 * n, n * (n - 1) // 2
+    per_stage = 43 * (NP * H_eta + n * H_mu) + 2 * D ** 3 + 4 * n * (n + 1) * D
+    return 4 * ode_steps * per_stage
+
+
+def hbm_bytes_per_walker_eloc(n, has_mu, ode_steps):
+    D, P = 2 * n, n * (n - 1) // 2 + (n if has_mu else 0)
+    return 8 * (D + 4 * ode_steps * (D + 3 * P) + 2 * D + 6)
+
+
+def build_model(args, dev):
+    from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
+    eta, mu = MLP(1, args.hidden), MLP(1, args.hidden)
+    # random-init weights of the reference architecture (FermionHO2D.py uses zeros, which
+    # would make the flow trivial; a 1e-2-scale Gaussian keeps every code path live)
+    g = torch.Generator().manual_seed(42)
+    with torch.no_grad():
+        for m in (eta, mu):
+            m.fc1.weight.copy_(torch.randn(m.fc1.weight.shape, generator=g))
+            m.fc1.bias.copy_(torch.randn(m.fc1.bias.shape, generator=g))
+            m.fc2.weight.copy_(1e-2 * torch.randn(m.fc2.weight.shape, generator=g))
+    cnf = CNF(Backflow(eta, mu=mu), (0.0, 1.0), nsteps=args.ode_steps)
+    model = GSVMC(args.nup, args.ndown, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(args.Z), sp_potential=HO())
+    return model.to(dev)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from fermiflow_b200 import _lib as L
+    import ctypes as C
+
+    model = build_model(args, dev)
+    model.basedist.manual_seed(1000 + rank)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    B = args.walkers
+    params = list(model.parameters())
+    nparam = sum(p.numel() for p in params)
+
+    # kernel-level timing of the dominant kernel (ff_eloc) with CUDA events on the launch stream
+    from fermiflow_b200 import utils as U
+    eloc_events = []
+    orig_sweep = U.eloc_sweep
+
+    def timed_sweep(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_sweep(*a, **k)
+        e1.record()
+        eloc_events.append((e0, e1))
+        return r
+    import fermiflow_b200.VMC as V
+    V.eloc_sweep = timed_sweep
+
+    def step():
+        gradE = model(B)
+        opt.zero_grad(set_to_none=True)
+        gradE.backward()
+        model.allreduce_gradients()
+        opt.step()
+        return model.E
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    # FP64 roofline denominator, measured on this device (MEASURED_PEAKS.json has no fp64 entry)
+    peak = C.c_double()
+    L.check(L.lib().ff_fp64_peak(20000, C.byref(peak), None))
+    eloc_events.clear()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    E = None
+    for _ in range(args.steps):
+        E = step()
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    eloc_ms = sum(a.elapsed_time(b) for a, b in eloc_events) / max(len(eloc_events), 1)
+
+    # end-to-end through the public API with HOST buffers: parameters come from pinned host
+    # memory every step, energy moments and the gradient go back to the host.
+    host_params = torch.cat([p.detach().reshape(-1) for p in params]).cpu().pin_memory()
+    host_out = torch.empty(nparam + 2, dtype=torch.float64).pin_memory()
+    dev_params = torch.empty(nparam, device=dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        dev_params.copy_(host_params, non_blocking=True)
+        o = 0
+        with torch.no_grad():
+            for p in params:
+                p.copy_(dev_params[o:o + p.numel()].view_as(p))
+                o += p.numel()
+        gradE = model(B)
+        opt.zero_grad(set_to_none=True)
+        gradE.backward()
+        model.allreduce_gradients()
+        flat = torch.cat([p.grad.reshape(-1) for p in params] +
+                         [torch.tensor([model.E, model.E_std], device=dev)])
+        host_out.copy_(flat, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    tms = torch.tensor([ms, e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = tms.tolist()
+    total_walkers = B * world * args.steps
+    value = total_walkers / (ms * 1e-3)
+    n = args.nup + args.ndown
+    fl = flops_per_walker_eloc(n, args.hidden, args.hidden, args.ode_steps) * B
+    by = hbm_bytes_per_walker_eloc(n, True, args.ode_steps) * B
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "ground-state 2D quantum dot N=%d (%d up/%d down), %d walkers per GPU, Z=%.1f, "
+                               "Deta=Dmu=%d, %d RK4 steps" % (n, args.nup, args.ndown, B, args.Z, args.hidden, args.ode_steps),
+                   "walkers_per_gpu": B, "ode_steps": args.ode_steps,
+                   "l2_policy": "inputs larger than L2 (per step: 21 MB coordinates, >20 GB stash streamed)",
+                   "parallelism": "walkers sharded, dp%d" % world},
+        "e2e": {"value": total_walkers / (e2e_ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": nparam * 8, "d2h_bytes_per_step": (nparam + 2) * 8},
+        "gpu_launches": 7 * args.steps,
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "fp64", "kernel": "ff::flow_kernel<MODE_ELOC>", "achieved": fl / (eloc_ms * 1e-3) / 1e12,
+                     "peak": peak.value / 1e12, "unit": "TFLOP/s", "frac": fl / (eloc_ms * 1e-3) / peak.value,
+                     "peak_source": "ff_fp64_peak DFMA microbenchmark on this device (MEASURED_PEAKS.json has no fp64 entry)",
+                     "traffic": None, "kernel_ms": eloc_ms,
+                     "hbm": {"achieved": by / (eloc_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": by / (eloc_ms * 1e-3) / 1e9 / hbm_peak}},
+        "energy": E,
+    }
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args, budget_s=25.0)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, budget_s):
+    """The reference's own algorithm (adaptive dopri5, adjoint, nested-autograd Laplacian)
+    ported to torch-CPU (oracle/reference_port.py), one VMC iteration on a small batch."""
+    from oracle import reference_port as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    walkers = args.ref_walkers
+    t = R.time_vmc_iteration(args.nup, args.ndown, args.hidden, args.Z, walkers, seed=7)
+    return {"value": walkers / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "1 VMC iteration of %d walkers, N=%d, reference algorithm (dopri5 rtol 1e-6 + adjoint + "
+                      "2N nested autograd passes), %.1f s" % (walkers, args.nup + args.ndown, t)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import reference_port as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    walkers = args.ref_walkers
+    n = args.nup + args.ndown
+    for _ in range(min(args.warmup, 1)):
+        R.time_vmc_iteration(args.nup, args.ndown, args.hidden, args.Z, 1, seed=1, equil=2)
+    ts = [R.time_vmc_iteration(args.nup, args.ndown, args.hidden, args.Z, walkers, seed=10 + i) for i in range(args.steps)]
+    tot = sum(ts)
+    value = walkers * args.steps / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "ground-state 2D quantum dot N=%d (%d up/%d down), Z=%.1f, Deta=Dmu=%d; bounded sample of "
+                               "%d walkers per step on the host CPU" % (n, args.nup, args.ndown, args.Z, args.hidden, walkers)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "%d VMC iterations of %d walkers (reference algorithm ported to torch-CPU: "
+                                   "oracle/reference_port.py)" % (args.steps, walkers)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

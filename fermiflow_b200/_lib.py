@@ -40,6 +40,7 @@ SIGNATURES = {
     "ff_potential": ([_P, _LL, _I, _D, _I, _P, _P], C.c_int),
     "ff_occupation_sample": ([_P, _I, _P, _LL, _P, _P, _P, _P], C.c_int),
     "ff_fp64_peak": ([_I, C.POINTER(_D), _P], C.c_int),
+    "ff_fp64_mma_peak": ([_I, C.POINTER(_D), _P], C.c_int),
 }
 
 

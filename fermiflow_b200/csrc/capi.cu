@@ -73,11 +73,12 @@ int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t
     a.P = a.NP + (m->H_mu > 0 ? n : 0);
     if (a.P < 1) return fail(-1, "a single particle without one-body backflow has no velocity field");
     const bool eloc = mode == ff::MODE_ELOC;
-    a.DP = eloc ? ((a.D + 3) / 4) * 4 + 2 : a.D;
-    a.NSV = eloc ? 3 * a.D + 2 + a.D * a.DP : a.D + (mode >= ff::MODE_DIV ? 1 : 0);
+    const int D8 = (a.D + 7) & ~7;
+    a.DP = eloc ? D8 + 4 : a.D;              // DP mod 16 in {4, 12}: conflict-free DMMA fragments
+    a.NSV = eloc ? 3 * a.D + 2 + D8 * a.DP : a.D + (mode >= ff::MODE_DIV ? 1 : 0);
     int off = even(5 * a.NSV);
     a.off_G = off; off = even(off + a.P * ff::kGRec);
-    a.off_AM = off; if (eloc) off = even(off + a.D * a.DP);
+    a.off_AM = off; if (eloc) off = even(off + D8 * a.DP);
     a.off_u = off; if (eloc) off += a.D;
     a.off_kLx = off; if (eloc) off += a.D;
     a.off_part = off; off = even(off + 2 * n);
@@ -88,7 +89,7 @@ int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t
         const int need = ff::slater_scratch_size(m->n_up, m->n_dn) + 2 * a.D + n * n + a.NP + 8;
         if (need > 4 * a.NSV) return fail(-2, "internal: finale scratch does not fit");
     }
-    int common = 64 + 6 * (m->H_eta + m->H_mu);
+    int common = 64 + 6 * (even(m->H_eta) + even(m->H_mu));
     common = even(common) + 2 * ((a.NP + 7) / 8) + 2;
     const long long budget = (long long)di.smem_optin / 8 - common;
     const int target_threads = eloc ? 512 : 256;

@@ -77,6 +77,13 @@ __constant__ double c_exp2_64[64] = {
     1.978456026387951
 };
 
+// exp() range-reduction constants, read through the constant bank so that ptxas folds them
+// into DFMA operands instead of re-materialising 64-bit immediates inside the hot loop.
+__constant__ double c_sig[8] = {92.33248261689366,        // 64 / ln 2
+                                0.01083042469326756,      // ln2/64, low 21 mantissa bits zero
+                                2.9815858269852933e-12,   // ln2/64 remainder
+                                1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.0, 0.0};
+
 __device__ __forceinline__ double rcp_approx(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));   // MUFU.RCP64H, >= 20 good bits
@@ -113,41 +120,79 @@ __device__ __forceinline__ double sigmoid_fast(double u, const double* __restric
     return fma(y, q, y);
 }
 
+// Two independent sigmoids in lock-step (explicit ILP 2: the FP64 pipe issues one warp
+// instruction every 2 cycles and each chain is ~14 dependent FP64 ops deep).
+__device__ __forceinline__ void sigmoid_fast2(double u0, double u1, const double* __restrict__ tab,
+                                              double& s0, double& s1) {
+    const double MAGIC = 6755399441055744.0;
+    const double L = c_sig[0], C_HI = c_sig[1], C_LO = c_sig[2];
+    double t0 = fma(u0, -L, MAGIC), t1 = fma(u1, -L, MAGIC);
+    double k0 = t0 - MAGIC, k1 = t1 - MAGIC;
+    double r0 = fma(k0, -C_HI, -u0), r1 = fma(k1, -C_HI, -u1);
+    r0 = fma(k0, -C_LO, r0); r1 = fma(k1, -C_LO, r1);
+    const int i0 = __double2loint(t0), i1 = __double2loint(t1);
+    const double T0 = tab[i0 & 63], T1 = tab[i1 & 63];
+    const double c5 = c_sig[3], c4 = c_sig[4], c3 = c_sig[5];
+    double p0 = fma(r0, c5, c4), p1 = fma(r1, c5, c4);
+    p0 = fma(p0, r0, c3); p1 = fma(p1, r1, c3);
+    p0 = fma(p0, r0, 0.5); p1 = fma(p1, r1, 0.5);
+    p0 = fma(p0, r0, 1.0); p1 = fma(p1, r1, 1.0);
+    p0 = fma(p0, r0, 1.0); p1 = fma(p1, r1, 1.0);
+    const int m0 = min(max(i0 >> 6, -1020), 1020), m1 = min(max(i1 >> 6, -1020), 1020);
+    double e0 = p0 * T0, e1 = p1 * T1;
+    e0 = __hiloint2double(__double2hiint(e0) + (m0 << 20), __double2loint(e0));
+    e1 = __hiloint2double(__double2hiint(e1) + (m1 << 20), __double2loint(e1));
+    const double d0 = 1.0 + e0, d1 = 1.0 + e1;
+    const double y0 = rcp_approx(d0), y1 = rcp_approx(d1);
+    double q0 = fma(-d0, y0, 1.0), q1 = fma(-d1, y1, 1.0);
+    q0 = fma(q0, q0, q0); q1 = fma(q1, q1, q1);
+    s0 = fma(y0, q0, y0); s1 = fma(y1, q1, y1);
+}
+
 // Radial MLP f(d) = sum_h w2_h sigmoid(w1_h d + b1_h) and its d-derivatives up to ORD.
 // coef: shared memory, 6 doubles per hidden unit {w1, b1, c0=w2, c1=w2 w1, c2=w2 w1^2,
-// c3=w2 w1^3}.  Restates MLP.forward / MLP.grad (MLP.py:30-45) for D_in = 1.
+// c3=w2 w1^3}; the table is padded to an even number of hidden units with zero rows.
+// Restates MLP.forward / MLP.grad (MLP.py:30-45) for D_in = 1.
 template <int ORD>
 __device__ __forceinline__ void radial_mlp(const double* __restrict__ coef, int H, double d,
                                            const double* __restrict__ tab, double (&f)[4]) {
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll 2
-    for (int h = 0; h < H; ++h) {
-        const double2 wb = *reinterpret_cast<const double2*>(coef + 6 * h);
-        const double2 c01 = *reinterpret_cast<const double2*>(coef + 6 * h + 2);
-        double s = sigmoid_fast(fma(wb.x, d, wb.y), tab);
-        a0 = fma(c01.x, s, a0);
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    const int H2 = (H + 1) & ~1;
+#pragma unroll 1
+    for (int h = 0; h < H2; h += 2) {
+        const double* c = coef + 6 * h;
+        const double2 wbA = *reinterpret_cast<const double2*>(c);
+        const double2 wbB = *reinterpret_cast<const double2*>(c + 6);
+        double sA, sB;
+        sigmoid_fast2(fma(wbA.x, d, wbA.y), fma(wbB.x, d, wbB.y), tab, sA, sB);
+        const double2 cA01 = *reinterpret_cast<const double2*>(c + 2);
+        const double2 cB01 = *reinterpret_cast<const double2*>(c + 8);
+        a0 = fma(cA01.x, sA, a0); b0 = fma(cB01.x, sB, b0);
         if (ORD >= 1) {
-            double s1 = fma(-s, s, s);                  // s (1 - s)
-            a1 = fma(c01.y, s1, a1);
+            const double sA1 = fma(-sA, sA, sA), sB1 = fma(-sB, sB, sB);       // s (1 - s)
+            a1 = fma(cA01.y, sA1, a1); b1 = fma(cB01.y, sB1, b1);
             if (ORD >= 2) {
-                const double2 c23 = *reinterpret_cast<const double2*>(coef + 6 * h + 4);
-                double s2 = s1 * fma(-2.0, s, 1.0);     // s1 (1 - 2 s)
-                a2 = fma(c23.x, s2, a2);
+                const double2 cA23 = *reinterpret_cast<const double2*>(c + 4);
+                const double2 cB23 = *reinterpret_cast<const double2*>(c + 10);
+                const double sA2 = sA1 * fma(-2.0, sA, 1.0), sB2 = sB1 * fma(-2.0, sB, 1.0);
+                a2 = fma(cA23.x, sA2, a2); b2 = fma(cB23.x, sB2, b2);
                 if (ORD >= 3) {
-                    double s3 = s1 * fma(-6.0, s1, 1.0);   // s1 (1 - 6 s1)
-                    a3 = fma(c23.y, s3, a3);
+                    const double sA3 = sA1 * fma(-6.0, sA1, 1.0), sB3 = sB1 * fma(-6.0, sB1, 1.0);
+                    a3 = fma(cA23.y, sA3, a3); b3 = fma(cB23.y, sB3, b3);
                 }
             }
         }
     }
-    f[0] = a0; f[1] = a1; f[2] = a2; f[3] = a3;
+    f[0] = a0 + b0; f[1] = a1 + b1; f[2] = a2 + b2; f[3] = a3 + b3;
 }
 
 // Fill the shared coefficient table from the three parameter vectors of one MLP.
 __device__ __forceinline__ void load_mlp_coef(double* coef, const double* w1, const double* b1,
                                               const double* w2, int H) {
-    for (int h = threadIdx.x; h < H; h += blockDim.x) {
-        double a = w1[h], b = b1[h], c = w2[h];
+    const int H2 = (H + 1) & ~1;
+    for (int h = threadIdx.x; h < H2; h += blockDim.x) {
+        double a = 0.0, b = 0.0, c = 0.0;
+        if (h < H) { a = w1[h]; b = b1[h]; c = w2[h]; }
         coef[6 * h + 0] = a;
         coef[6 * h + 1] = b;
         coef[6 * h + 2] = c;
@@ -167,20 +212,33 @@ __device__ __forceinline__ int pair_index(int i, int j, int n) {
 // psi', psi'' for a = 0..7 via the three-term recursion
 //   h_{k+1} = sqrt(2/(k+1)) x h_k - sqrt(k/(k+1)) h_{k-1},  h_a' = sqrt(2a) h_{a-1},
 //   psi_a'' = (x^2 - 2a - 1) psi_a.
-struct Herm1D { double v[8], d1[8], d2[8]; };
+struct Herm1D { double v, d1, d2; };
 
-__device__ __forceinline__ void hermite_1d(double x, int amax, Herm1D& o) {
+// value / first / second derivative of psi_a(x) for the single order a (no arrays: the
+// recursion runs to a and the three numbers are picked up on the way).
+__device__ __forceinline__ Herm1D hermite_1d(double x, int a) {
+    const double g = exp(-0.5 * x * x);
+    double hm = 0.0, h = 1.0;
+    for (int k = 0; k < a; ++k) {
+        const double hn = sqrt(2.0 / (k + 1.0)) * x * h - sqrt(k / (k + 1.0)) * hm;
+        hm = h; h = hn;
+    }
+    Herm1D o;
+    o.v = h * g;
+    o.d1 = (sqrt(2.0 * a) * hm - x * h) * g;
+    o.d2 = (x * x - (2.0 * a + 1.0)) * h * g;
+    return o;
+}
+
+// all orders 0..7 of psi_a(x) (values only) for the Metropolis sampler
+__device__ __forceinline__ void hermite_values(double x, double (&v)[8]) {
     const double g = exp(-0.5 * x * x);
     double hm = 0.0, h = 1.0;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
-        if (a <= amax) {
-            o.v[a] = h * g;
-            o.d1[a] = (sqrt(2.0 * a) * hm - x * h) * g;
-            o.d2[a] = (x * x - (2.0 * a + 1.0)) * h * g;
-            double hn = sqrt(2.0 / (a + 1.0)) * x * h - sqrt(a / (a + 1.0)) * hm;
-            hm = h; h = hn;
-        }
+        v[a] = h * g;
+        const double hn = sqrt(2.0 / (a + 1.0)) * x * h - sqrt(a / (a + 1.0)) * hm;
+        hm = h; h = hn;
     }
 }
 
@@ -188,6 +246,13 @@ __constant__ unsigned char c_orb_nx[kMaxOrb] = {
     0, 0,1, 0,1,2, 0,1,2,3, 0,1,2,3,4, 0,1,2,3,4,5, 0,1,2,3,4,5,6, 0,1,2,3,4,5,6,7};
 __constant__ unsigned char c_orb_ny[kMaxOrb] = {
     0, 1,0, 2,1,0, 3,2,1,0, 4,3,2,1,0, 5,4,3,2,1,0, 6,5,4,3,2,1,0, 7,6,5,4,3,2,1,0};
+
+// D(8x8) += A(8x4) * B(4x8) on the FP64 tensor cores (DMMA).  Lane l holds A[l/4][l%4],
+// B[l%4][l/4] and D[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 // ---- Philox4x32-10 (Salmon et al. SC'11) ---------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {

@@ -52,6 +52,8 @@ struct FlowArgs {
 // Hessian contraction <H0, J J^T>, then assemble
 //   log p = log p0 - Delta,  grad = J^T g0 - gDelta,  lap = <H0, JJ^T> + g0.L - lapDelta,
 //   E_loc = -1/4 lap - 1/8 |grad|^2 + V(x)                       (VMC.py:48-55).
+__device__ __forceinline__ void gram_dmma(int W, int D8, int DP, double* wbase, int wstride, int oJ, int off_AM);
+
 __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
                             const unsigned char* pair_i, const unsigned char* pair_j) {
     const int tid = threadIdx.x, T = blockDim.x;
@@ -69,26 +71,8 @@ __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
         [&](int w) { long long b = base + w; int row = (a.walker_state && b < a.B) ? a.walker_state[b] : 0;
                      return a.orb + (size_t)row * n; });
 
-    // M = J J^T at the end point (upper blocks), into the AM buffer
-    {
-        const int ntile = n * (n + 1) / 2;
-        for (int g = tid; g < W * ntile; g += T) {
-            int w = g / ntile, t = g - w * ntile;
-            int i, j;
-            if (t < NP) { i = pair_i[t]; j = pair_j[t]; } else { i = j = t - NP; }
-            const double* J = S_in(w) + oJ;
-            const double* a0 = J + (2 * i) * DP; const double* a1 = a0 + DP;
-            const double* b0 = J + (2 * j) * DP; const double* b1 = b0 + DP;
-            double m00 = 0, m01 = 0, m10 = 0, m11 = 0;
-            for (int c = 0; c < D; ++c) {
-                m00 = fma(a0[c], b0[c], m00); m01 = fma(a0[c], b1[c], m01);
-                m10 = fma(a1[c], b0[c], m10); m11 = fma(a1[c], b1[c], m11);
-            }
-            double* M = S_in(w) + a.off_AM;
-            M[(2 * i) * DP + 2 * j] = m00; M[(2 * i) * DP + 2 * j + 1] = m01;
-            M[(2 * i + 1) * DP + 2 * j] = m10; M[(2 * i + 1) * DP + 2 * j + 1] = m11;
-        }
-    }
+    // M = J J^T at the end point (upper block triangle), into the AM buffer
+    gram_dmma(W, (D + 7) & ~7, DP, wbase, a.wstride, oJ, a.off_AM);
     // g0 and the per-(i,j) Hessian contraction terms
     for (int s = 0; s < 2; ++s) {
         const SlBlk blk = slater_blk(s, n, a.n_up);
@@ -183,24 +167,47 @@ __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
     __syncthreads();
 }
 
+// Gram matrix M = J J^T of every walker on the FP64 tensor cores: upper block triangle of
+// 8x8 blocks, one warp per block, K loop of D8/4 DMMAs.  J: [D8][DP] (rows >= D zero).
+__device__ __forceinline__ void gram_dmma(int W, int D8, int DP, double* wbase, int wstride, int oJ, int off_AM) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3, NB = D8 >> 3, ntri = NB * (NB + 1) / 2;
+    for (int task = warp; task < W * ntri; task += nwarp) {
+        const int w = task / ntri;
+        int rem = task - w * ntri, rb = 0;
+        while (rem >= NB - rb) { rem -= NB - rb; ++rb; }
+        const int cb = rb + rem;
+        const double* J = wbase + (size_t)w * wstride + oJ;
+        const double* A = J + (8 * rb + g) * DP + t;
+        const double* B = J + (8 * cb + g) * DP + t;
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll 2
+        for (int k = 0; k < D8; k += 4) dmma_m8n8k4(c0, c1, A[k], B[k]);
+        double* M = wbase + (size_t)w * wstride + off_AM + (8 * rb + g) * DP + 8 * cb + 2 * t;
+        *reinterpret_cast<double2*>(M) = make_double2(c0, c1);
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, T = blockDim.x;
     const int n = a.n, D = a.D, DP = a.DP, P = a.P, NP = a.NP, W = a.W, NSV = a.NSV;
-    (void)DP;
+    const int D8 = (D + 7) & ~7;
+    (void)DP; (void)D8;
     const bool has_mu = a.H_mu > 0;
+    const int warp = tid >> 5, lane = tid & 31, nwarp = T >> 5;
 
     // ---- shared carve-up -------------------------------------------------------------
     double* tab = smem;                               // 64
-    double* coef_eta = tab + 64;                      // 6 H_eta
-    double* coef_mu = coef_eta + 6 * a.H_eta;         // 6 H_mu
-    int cbase = 64 + 6 * (a.H_eta + a.H_mu);
-    cbase = (cbase + 1) & ~1;
+    double* coef_eta = tab + 64;                      // 6 * even(H_eta)
+    double* coef_mu = coef_eta + 6 * ((a.H_eta + 1) & ~1);
+    int cbase = 64 + 6 * (((a.H_eta + 1) & ~1) + ((a.H_mu + 1) & ~1));
     unsigned char* pair_i = reinterpret_cast<unsigned char*>(smem + cbase);   // NP each
     unsigned char* pair_j = pair_i + ((NP + 7) & ~7);
     double* wbase = smem + cbase + 2 * ((NP + 7) / 8);
     if ((wbase - smem) & 1) wbase += 1;
+    const int wstride = a.wstride;
 
     for (int i = tid; i < 64; i += T) tab[i] = c_exp2_64[i];
     load_mlp_coef(coef_eta, a.eta_w1, a.eta_b1, a.eta_w2, a.H_eta);
@@ -214,22 +221,16 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
 
     const double h = (a.tb - a.ta) / a.nsteps;
     const int NS = 4 * a.nsteps;
-
-    // per-walker block pointers
-    auto S_in = [&](int w) { return wbase + (size_t)w * a.wstride; };
-    auto P3 = [&](int w) { return S_in(w) + NSV; };
-    auto P4 = [&](int w) { return S_in(w) + 2 * NSV; };
-    auto PO = [&](int w) { return S_in(w) + 3 * NSV; };
-    auto KK = [&](int w) { return S_in(w) + 4 * NSV; };
-    auto GG = [&](int w) { return S_in(w) + a.off_G; };
     constexpr int oY = 0;
     const int oL = D, oG = 2 * D, oS = 3 * D, oJ = 3 * D + 2;       // ELOC offsets
     const int oDelta = (MODE == MODE_ELOC) ? oS : D;
+    const int oP3 = NSV, oP4 = 2 * NSV, oPO = 3 * NSV, oK = 4 * NSV;
 
     // item owned by this thread
     const int it_w = tid / P, it_p = tid - it_w * P;
     const bool it_valid = it_w < W;
     const bool it_pair = it_p < NP;
+    double* const myS = wbase + (size_t)(it_valid ? it_w : 0) * wstride;
     int it_i = 0, it_j = 0;
 
     for (long long base = (long long)blockIdx.x * W; base < a.B; base += (long long)gridDim.x * W) {
@@ -239,37 +240,41 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
             else { it_i = it_p - NP; it_j = it_i; }
         }
         // ---- load walkers, initialise state -------------------------------------------
-        for (int g = tid; g < W * NSV; g += T) {
-            int w = g / NSV, e = g - w * NSV;
-            long long b = base + w;
-            double v = 0.0;
-            if (e < D) {
-                // padding walkers get a harmless, well separated configuration
-                v = (b < a.B) ? a.x_in[b * D + e] : (double)(e >> 1) + 0.37 * (e & 1);
-            } else if (MODE == MODE_ELOC && e >= oJ) {
-                int r = (e - oJ) / DP, c = (e - oJ) - r * DP;
-                v = (r == c) ? 1.0 : 0.0;
+        for (int w = 0; w < W; ++w) {
+            double* Sw = wbase + (size_t)w * wstride;
+            const long long b = base + w;
+            for (int e = tid; e < NSV; e += T) {
+                double v = 0.0;
+                if (e < D) {
+                    // padding walkers get a harmless, well separated configuration
+                    v = (b < a.B) ? a.x_in[b * D + e] : (double)(e >> 1) + 0.37 * (e & 1);
+                    if (MODE == MODE_ELOC) (Sw + a.off_x0)[e] = v;
+                } else if (MODE == MODE_ELOC && e >= oJ) {
+                    const int r = (e - oJ) / DP, c = (e - oJ) - r * DP;
+                    v = (r == c && r < D) ? 1.0 : 0.0;
+                }
+                Sw[e] = v;
             }
-            S_in(w)[e] = v;
-            if (MODE == MODE_ELOC && e < D) (S_in(w) + a.off_x0)[e] = v;
+            if (MODE == MODE_ELOC)
+                for (int e = tid; e < D8 * DP; e += T) (Sw + a.off_AM)[e] = 0.0;
         }
         __syncthreads();
 
         for (int stage = 0; stage < NS; ++stage) {
             const int sub = stage & 3;
-            // ======== S0: per-item radial functions (+ SYRK for ELOC) =====================
+            // ======== S0: per-item radial functions (+ Gram matrix for ELOC) ==============
             double rx = 0, ry = 0, ca = 0, cb = 0, ccq = 0, ceq = 0, cf = 0;
             if (it_valid) {
-                const double* y = S_in(it_w) + oY;
+                const double* y = myS + oY;
                 if (it_pair) { rx = y[2 * it_i] - y[2 * it_j]; ry = y[2 * it_i + 1] - y[2 * it_j + 1]; }
                 else { rx = y[2 * it_i]; ry = y[2 * it_i + 1]; }
                 const double d2 = fma(rx, rx, ry * ry);
                 const double d = sqrt(d2);
                 double f[4];
                 constexpr int ORD = (MODE == MODE_V) ? 0 : (MODE == MODE_DIV) ? 1 : (MODE == MODE_STASH) ? 2 : 3;
-                if (it_pair) radial_mlp<ORD>(coef_eta, a.H_eta, d, tab, f);
-                else radial_mlp<ORD>(coef_mu, a.H_mu, d, tab, f);
-                double* G = GG(it_w) + it_p * kGRec;
+                // one call for both item kinds: no divergence between pair and single lanes
+                radial_mlp<ORD>(it_pair ? coef_eta : coef_mu, it_pair ? a.H_eta : a.H_mu, d, tab, f);
+                double* G = myS + a.off_G + it_p * kGRec;
                 cf = f[0];
                 G[0] = cf * rx;
                 G[1] = cf * ry;
@@ -301,41 +306,19 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                 }
             }
             if (MODE >= MODE_STASH && a.stash_y != nullptr) {
-                for (int g = tid; g < W * D; g += T) {
-                    int w = g / D, e = g - w * D;
-                    long long b = base + w;
-                    if (b < a.B) a.stash_y[(b * NS + stage) * D + e] = S_in(w)[e];
+                for (int w = 0; w < W; ++w) {
+                    const long long b = base + w;
+                    if (b < a.B)
+                        for (int e = tid; e < D; e += T)
+                            a.stash_y[(b * NS + stage) * D + e] = (wbase + (size_t)w * wstride)[e];
                 }
             }
             if (MODE == MODE_ELOC) {
-                // M = J J^T (upper 2x2 blocks i <= j), one (walker, i, j) tile per loop trip
-                const int ntile = n * (n + 1) / 2;
-                for (int g = tid; g < W * ntile; g += T) {
-                    int w = g / ntile, t = g - w * ntile;
-                    int i, j;
-                    if (t < NP) { i = pair_i[t]; j = pair_j[t]; } else { i = j = t - NP; }
-                    const double* J = S_in(w) + oJ;
-                    const double* a0 = J + (2 * i) * DP; const double* a1 = a0 + DP;
-                    const double* b0 = J + (2 * j) * DP; const double* b1 = b0 + DP;
-                    double m00 = 0, m01 = 0, m10 = 0, m11 = 0;
-                    for (int c = 0; c < D; c += 2) {
-                        double2 x0 = *reinterpret_cast<const double2*>(a0 + c);
-                        double2 x1 = *reinterpret_cast<const double2*>(a1 + c);
-                        double2 z0 = *reinterpret_cast<const double2*>(b0 + c);
-                        double2 z1 = *reinterpret_cast<const double2*>(b1 + c);
-                        m00 = fma(x0.x, z0.x, m00); m00 = fma(x0.y, z0.y, m00);
-                        m01 = fma(x0.x, z1.x, m01); m01 = fma(x0.y, z1.y, m01);
-                        m10 = fma(x1.x, z0.x, m10); m10 = fma(x1.y, z0.y, m10);
-                        m11 = fma(x1.x, z1.x, m11); m11 = fma(x1.y, z1.y, m11);
-                    }
-                    double* M = S_in(w) + a.off_AM;
-                    M[(2 * i) * DP + 2 * j] = m00; M[(2 * i) * DP + 2 * j + 1] = m01;
-                    M[(2 * i + 1) * DP + 2 * j] = m10; M[(2 * i + 1) * DP + 2 * j + 1] = m11;
-                }
+                gram_dmma(W, D8, DP, wbase, wstride, oJ, a.off_AM);
                 __syncthreads();
                 // ======== S1: second-derivative contractions per item ====================
                 if (it_valid) {
-                    const double* M = S_in(it_w) + a.off_AM;
+                    const double* M = myS + a.off_AM;
                     const int i2 = 2 * it_i, j2 = 2 * it_j;
                     double w00, w01, w11;
                     if (it_pair) {
@@ -347,7 +330,7 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                     }
                     const double wrx = fma(w00, rx, w01 * ry), wry = fma(w01, rx, w11 * ry);
                     const double trw = w00 + w11, rwr = fma(rx, wrx, ry * wry);
-                    double* G = GG(it_w) + it_p * kGRec;
+                    double* G = myS + a.off_G + it_p * kGRec;
                     G[4] = fma(ca, fma(2.0, wrx, trw * rx), cb * rwr * rx);
                     G[5] = fma(ca, fma(2.0, wry, trw * ry), cb * rwr * ry);
                     G[7] = fma(ccq, trw, ceq * rwr);
@@ -357,35 +340,38 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
             // ======== S2: gather per particle, build Jacobian matrix ======================
             {
                 constexpr int NC = (MODE == MODE_ELOC) ? kGRec : (MODE >= MODE_DIV ? 3 : 2);
-                for (int g = tid; g < W * n * NC; g += T) {
-                    int w = g / (n * NC), rem = g - w * (n * NC);
-                    int i = rem / NC, cc = rem - i * NC;
-                    int c = (MODE == MODE_ELOC) ? cc : (cc == 2 ? 6 : cc);
-                    const double* G = GG(w);
-                    double acc = 0.0;
-                    const bool odd = c < 6;
-                    const double wgt = (c == 6 || c == 7) ? 0.5 : 1.0;
-                    for (int j = 0; j < i; ++j) {
-                        double v = G[pair_index(j, i, n) * kGRec + c];
-                        acc += odd ? -v : v;
-                    }
-                    for (int j = i + 1; j < n; ++j) acc += G[pair_index(i, j, n) * kGRec + c];
-                    acc *= wgt;
-                    if (has_mu) acc += G[(NP + i) * kGRec + c];
-                    double* Sw = S_in(w);
-                    if (c < 2) KK(w)[oY + 2 * i + c] = acc;
-                    else if (c < 4) (Sw + a.off_u)[2 * i + c - 2] = acc;
-                    else if (c < 6) (Sw + a.off_kLx)[2 * i + c - 4] = acc;
-                    else if (c < 8) (Sw + a.off_part)[(c - 6) * n + i] = acc;
-                    else {
-                        double* A = Sw + a.off_AM;
-                        if (c == 8) A[(2 * i) * DP + 2 * i] = acc;
-                        else if (c == 9) { A[(2 * i) * DP + 2 * i + 1] = acc; A[(2 * i + 1) * DP + 2 * i] = acc; }
-                        else A[(2 * i + 1) * DP + 2 * i + 1] = acc;
+                for (int w = 0; w < W; ++w) {
+                    double* Sw = wbase + (size_t)w * wstride;
+                    const double* G = Sw + a.off_G;
+                    for (int g = tid; g < n * NC; g += T) {
+                        const int i = g / NC, cc = g - i * NC;
+                        const int c = (MODE == MODE_ELOC) ? cc : (cc == 2 ? 6 : cc);
+                        double accm = 0.0, accp = 0.0;
+                        {   // pairs (j, i), j < i : stored with r = y_j - y_i
+                            int idx = i - 1;                       // pair_index(0, i)
+                            for (int j = 0; j < i; ++j) { accm += G[idx * kGRec + c]; idx += n - j - 2; }
+                        }
+                        {   // pairs (i, j), j > i : consecutive
+                            const double* Gi = G + pair_index(i, i + 1, n) * kGRec + c;
+                            for (int j = i + 1; j < n; ++j) { accp += *Gi; Gi += kGRec; }
+                        }
+                        double acc = (c < 6) ? accp - accm : accp + accm;
+                        if (c == 6 || c == 7) acc *= 0.5;
+                        if (has_mu) acc += G[(NP + i) * kGRec + c];
+                        if (c < 2) (Sw + oK)[oY + 2 * i + c] = acc;
+                        else if (c < 4) (Sw + a.off_u)[2 * i + c - 2] = acc;
+                        else if (c < 6) (Sw + a.off_kLx)[2 * i + c - 4] = acc;
+                        else if (c < 8) (Sw + a.off_part)[(c - 6) * n + i] = acc;
+                        else {
+                            double* A = Sw + a.off_AM;
+                            if (c == 8) A[(2 * i) * DP + 2 * i] = acc;
+                            else if (c == 9) { A[(2 * i) * DP + 2 * i + 1] = acc; A[(2 * i + 1) * DP + 2 * i] = acc; }
+                            else A[(2 * i + 1) * DP + 2 * i + 1] = acc;
+                        }
                     }
                 }
                 if (MODE == MODE_ELOC && it_valid && it_pair) {
-                    double* A = S_in(it_w) + a.off_AM;
+                    double* A = myS + a.off_AM;
                     const double a00 = -fma(ca * rx, rx, cf), a01 = -(ca * rx * ry), a11 = -fma(ca * ry, ry, cf);
                     const int i2 = 2 * it_i, j2 = 2 * it_j;
                     A[i2 * DP + j2] = a00; A[i2 * DP + j2 + 1] = a01;
@@ -397,102 +383,108 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
             __syncthreads();
             // ======== S3: derivative of the whole state ===================================
             if (MODE == MODE_ELOC) {
-                // K.J = A * J : 2 x 4 register tiles
-                const int ncg = (D + 3) / 4;
-                for (int g = tid; g < W * n * ncg; g += T) {
-                    int w = g / (n * ncg), rem = g - w * (n * ncg);
-                    int i = rem / ncg, cg = rem - i * ncg;
-                    const double* A = S_in(w) + a.off_AM;        // symmetric: column 2i.. read as row
-                    const double* J = S_in(w) + oJ + 4 * cg;
-                    double k00 = 0, k01 = 0, k02 = 0, k03 = 0, k10 = 0, k11 = 0, k12 = 0, k13 = 0;
-#pragma unroll 4
-                    for (int k = 0; k < D; ++k) {
-                        double2 av = *reinterpret_cast<const double2*>(A + k * DP + 2 * i);
-                        double2 b01 = *reinterpret_cast<const double2*>(J + k * DP);
-                        double2 b23 = *reinterpret_cast<const double2*>(J + k * DP + 2);
-                        k00 = fma(av.x, b01.x, k00); k01 = fma(av.x, b01.y, k01);
-                        k02 = fma(av.x, b23.x, k02); k03 = fma(av.x, b23.y, k03);
-                        k10 = fma(av.y, b01.x, k10); k11 = fma(av.y, b01.y, k11);
-                        k12 = fma(av.y, b23.x, k12); k13 = fma(av.y, b23.y, k13);
+                // K.J = A * J on the FP64 tensor cores: one warp per 8x8 output block
+                {
+                    const int g = lane >> 2, t = lane & 3, NB = D8 >> 3;
+                    for (int task = warp; task < W * NB * NB; task += nwarp) {
+                        const int w = task / (NB * NB), rem = task - w * NB * NB;
+                        const int rb = rem / NB, cbk = rem - rb * NB;
+                        double* Sw = wbase + (size_t)w * wstride;
+                        const double* Ap = Sw + a.off_AM + (8 * rb + g) * DP + t;     // A[row][k]
+                        const double* Bp = Sw + oJ + t * DP + 8 * cbk + g;            // J[k][col]
+                        double c0 = 0.0, c1 = 0.0;
+#pragma unroll 2
+                        for (int k = 0; k < D8; k += 4) dmma_m8n8k4(c0, c1, Ap[k], Bp[k * DP]);
+                        double* K = Sw + oK + oJ + (8 * rb + g) * DP + 8 * cbk + 2 * t;
+                        *reinterpret_cast<double2*>(K) = make_double2(c0, c1);
                     }
-                    double* K = KK(w) + oJ + (2 * i) * DP + 4 * cg;
-                    *reinterpret_cast<double2*>(K) = make_double2(k00, k01);
-                    *reinterpret_cast<double2*>(K + 2) = make_double2(k02, k03);
-                    *reinterpret_cast<double2*>(K + DP) = make_double2(k10, k11);
-                    *reinterpret_cast<double2*>(K + DP + 2) = make_double2(k12, k13);
                 }
                 // K.L = A L + kLx ;  K.gD = -(u^T J)
-                for (int g = tid; g < W * 2 * D; g += T) {
-                    int w = g / (2 * D), e = g - w * 2 * D;
-                    const double* Sw = S_in(w);
-                    if (e < D) {
-                        const double* A = Sw + a.off_AM + e * DP;
-                        const double* L = Sw + oL;
-                        double acc = (Sw + a.off_kLx)[e];
-                        for (int k = 0; k < D; ++k) acc = fma(A[k], L[k], acc);
-                        KK(w)[oL + e] = acc;
-                    } else {
-                        int c = e - D;
-                        const double* u = Sw + a.off_u;
-                        const double* J = Sw + oJ + c;
-                        double acc = 0.0;
-                        for (int k = 0; k < D; ++k) acc = fma(u[k], J[k * DP], acc);
-                        KK(w)[oG + c] = -acc;
+                for (int w = 0; w < W; ++w) {
+                    double* Sw = wbase + (size_t)w * wstride;
+                    for (int e = tid; e < 2 * D; e += T) {
+                        if (e < D) {
+                            const double* A = Sw + a.off_AM + e * DP;
+                            const double* L = Sw + oL;
+                            double acc0 = (Sw + a.off_kLx)[e], acc1 = 0.0;
+                            for (int k = 0; k < D; k += 2) {
+                                const double2 av = *reinterpret_cast<const double2*>(A + k);
+                                const double2 lv = *reinterpret_cast<const double2*>(L + k);
+                                acc0 = fma(av.x, lv.x, acc0); acc1 = fma(av.y, lv.y, acc1);
+                            }
+                            (Sw + oK)[oL + e] = acc0 + acc1;
+                        } else {
+                            const int c = e - D;
+                            const double* u = Sw + a.off_u;
+                            const double* J = Sw + oJ + c;
+                            double acc0 = 0.0, acc1 = 0.0;
+                            for (int k = 0; k < D; k += 2) {
+                                acc0 = fma(u[k], J[k * DP], acc0);
+                                acc1 = fma(u[k + 1], J[(k + 1) * DP], acc1);
+                            }
+                            (Sw + oK)[oG + c] = -(acc0 + acc1);
+                        }
                     }
                 }
-                for (int w = tid; w < W; w += T) {
-                    const double* Sw = S_in(w);
+                // scalar rates: one warp per walker, shuffle reductions
+                for (int w = nwarp - 1 - warp; w < W && w >= 0; w += nwarp) {
+                    double* Sw = wbase + (size_t)w * wstride;
                     const double* part = Sw + a.off_part;
-                    double rho = 0.0, lp = 0.0;
-                    for (int i = 0; i < n; ++i) { rho += part[i]; lp += part[n + i]; }
                     const double* u = Sw + a.off_u; const double* L = Sw + oL;
-                    for (int k = 0; k < D; ++k) lp = fma(u[k], L[k], lp);
-                    KK(w)[oS] = -rho;
-                    KK(w)[oS + 1] = -lp;
+                    double rho = 0.0, lp = 0.0;
+                    for (int i = lane; i < n; i += 32) { rho += part[i]; lp += part[n + i]; }
+                    for (int k = lane; k < D; k += 32) lp = fma(u[k], L[k], lp);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        rho += __shfl_xor_sync(0xffffffffu, rho, o);
+                        lp += __shfl_xor_sync(0xffffffffu, lp, o);
+                    }
+                    if (lane == 0) { (Sw + oK)[oS] = -rho; (Sw + oK)[oS + 1] = -lp; }
                 }
             } else if (MODE >= MODE_DIV) {
                 for (int w = tid; w < W; w += T) {
-                    const double* part = S_in(w) + a.off_part;
+                    double* Sw = wbase + (size_t)w * wstride;
+                    const double* part = Sw + a.off_part;
                     double rho = 0.0;
                     for (int i = 0; i < n; ++i) rho += part[i];
-                    KK(w)[oDelta] = -rho;
+                    (Sw + oK)[oDelta] = -rho;
                 }
             }
             __syncthreads();
             // ======== S4: 3/8-rule RK4 bookkeeping (torchdiffeq rk4_alt_step_func) ========
-            for (int g = tid; g < W * NSV; g += T) {
-                int w = g / NSV, e = g - w * NSV;
-                double* s = S_in(w) + e;
-                const double k = KK(w)[e] * h;
-                if (sub == 0) {
-                    const double y0 = *s;
-                    P3(w)[e] = fma(k, -1.0 / 3.0, y0);
-                    P4(w)[e] = y0 + k;
-                    PO(w)[e] = fma(k, 0.125, y0);
-                    *s = fma(k, 1.0 / 3.0, y0);
-                } else if (sub == 1) {
-                    *s = P3(w)[e] + k;
-                    P4(w)[e] -= k;
-                    PO(w)[e] = fma(k, 0.375, PO(w)[e]);
-                } else if (sub == 2) {
-                    *s = P4(w)[e] + k;
-                    PO(w)[e] = fma(k, 0.375, PO(w)[e]);
-                } else {
-                    *s = fma(k, 0.125, PO(w)[e]);
+            for (int w = 0; w < W; ++w) {
+                double* Sw = wbase + (size_t)w * wstride;
+                for (int e = tid; e < NSV; e += T) {
+                    const double k = Sw[oK + e] * h;
+                    if (sub == 0) {
+                        const double y0 = Sw[e];
+                        Sw[oP3 + e] = fma(k, -1.0 / 3.0, y0);
+                        Sw[oP4 + e] = y0 + k;
+                        Sw[oPO + e] = fma(k, 0.125, y0);
+                        Sw[e] = fma(k, 1.0 / 3.0, y0);
+                    } else if (sub == 1) {
+                        Sw[e] = Sw[oP3 + e] + k;
+                        Sw[oP4 + e] -= k;
+                        Sw[oPO + e] = fma(k, 0.375, Sw[oPO + e]);
+                    } else if (sub == 2) {
+                        Sw[e] = Sw[oP4 + e] + k;
+                        Sw[oPO + e] = fma(k, 0.375, Sw[oPO + e]);
+                    } else {
+                        Sw[e] = fma(k, 0.125, Sw[oPO + e]);
+                    }
                 }
             }
             __syncthreads();
         }   // stages
 
         // ---- outputs ----------------------------------------------------------------------
-        for (int g = tid; g < W * D; g += T) {
-            int w = g / D, e = g - w * D;
-            long long b = base + w;
-            if (b < a.B && a.y_out) a.y_out[b * D + e] = S_in(w)[e];
-        }
-        if (MODE >= MODE_DIV) {
-            for (int w = tid; w < W; w += T)
-                if (base + w < a.B && a.delta_out) a.delta_out[base + w] = S_in(w)[oDelta];
+        for (int w = 0; w < W; ++w) {
+            const long long b = base + w;
+            const double* Sw = wbase + (size_t)w * wstride;
+            if (b < a.B) {
+                if (a.y_out) for (int e = tid; e < D; e += T) a.y_out[b * D + e] = Sw[e];
+                if (MODE >= MODE_DIV && a.delta_out && tid == 0) a.delta_out[b] = Sw[oDelta];
+            }
         }
         if (MODE == MODE_ELOC) eloc_finale(a, base, wbase, pair_i, pair_j);
     }

@@ -28,8 +28,8 @@ __global__ void __launch_bounds__(512) backflow_kernel(const BackflowArgs a) {
     const bool has_mu = a.H_mu > 0;
     double* tab = smem;
     double* coef_eta = tab + 64;
-    double* coef_mu = coef_eta + 6 * a.H_eta;
-    double* wb = coef_mu + 6 * a.H_mu;
+    double* coef_mu = coef_eta + 6 * ((a.H_eta + 1) & ~1);
+    double* wb = coef_mu + 6 * ((a.H_mu + 1) & ~1);
     const int wstride = D + 3 * P;          // x[D], G[P][3] (vx, vy, q)
     for (int i = tid; i < 64; i += T) tab[i] = c_exp2_64[i];
     load_mlp_coef(coef_eta, a.eta_w1, a.eta_b1, a.eta_w2, a.H_eta);
@@ -56,8 +56,7 @@ __global__ void __launch_bounds__(512) backflow_kernel(const BackflowArgs a) {
             } else { const int i = it_p - NP; rx = x[2 * i]; ry = x[2 * i + 1]; }
             const double d = sqrt(fma(rx, rx, ry * ry));
             double f[4];
-            if (pair) radial_mlp<1>(coef_eta, a.H_eta, d, tab, f);
-            else radial_mlp<1>(coef_mu, a.H_mu, d, tab, f);
+            radial_mlp<1>(pair ? coef_eta : coef_mu, pair ? a.H_eta : a.H_mu, d, tab, f);
             G[0] = f[0] * rx; G[1] = f[0] * ry;
             G[2] = (pair ? 2.0 : 1.0) * fma(f[1], d, 2.0 * f[0]);
         }
@@ -186,15 +185,15 @@ __device__ __forceinline__ double metro_logdet(const double* X, int xs, int i0, 
                                                double* A, size_t sa) {
     const double inv_sqrt_pi = 0.56418958354775628695;
     for (int r = 0; r < ns; ++r) {
-        Herm1D hx, hy;
-        hermite_1d(X[(size_t)(2 * (i0 + r)) * xs], 7, hx);
-        hermite_1d(X[(size_t)(2 * (i0 + r) + 1) * xs], 7, hy);
+        double hxv[8], hyv[8];
+        hermite_values(X[(size_t)(2 * (i0 + r)) * xs], hxv);
+        hermite_values(X[(size_t)(2 * (i0 + r) + 1) * xs], hyv);
         for (int c = 0; c < ns; ++c) {
             const int id = orb[i0 + c];
             const int nx = c_orb_nx[id], ny = c_orb_ny[id];
             double vx = 0, vy = 0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) { if (q == nx) vx = hx.v[q]; if (q == ny) vy = hy.v[q]; }
+            for (int q = 0; q < 8; ++q) { if (q == nx) vx = hxv[q]; if (q == ny) vy = hyv[q]; }
             A[(size_t)(r * ns + c) * sa] = inv_sqrt_pi * vx * vy;
         }
     }
@@ -354,6 +353,22 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, 
         }
     }
     double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[0] = s;
+}
+
+
+// DMMA (mma.sync m8n8k4 f64) throughput probe: 4 independent accumulator tiles per warp.
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double seed, double* sink) {
+    double c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const double a = seed + threadIdx.x * 1e-9, b = 1.0000001;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            dmma_m8n8k4(c[0], c[1], a, b); dmma_m8n8k4(c[2], c[3], a, b);
+            dmma_m8n8k4(c[4], c[5], a, b); dmma_m8n8k4(c[6], c[7], a, b);
+        }
+    }
+    double s = c[0] + c[1] + c[2] + c[3] + c[4] + c[5] + c[6] + c[7];
     if (s == 123.456) sink[0] = s;
 }
 

@@ -57,15 +57,8 @@ __device__ void slater_team(int W, int n, int n_up, ZPtr zptr, SPtr sptr, OrbPtr
             const double* z = zptr(w) + 2 * (blk.i0 + i);
             const int id = orbptr(w)[blk.i0 + k];
             const int nx = c_orb_nx[id], ny = c_orb_ny[id];
-            Herm1D hx, hy;
-            hermite_1d(z[0], nx, hx);
-            hermite_1d(z[1], ny, hy);
-            double vx = 0, vx1 = 0, vx2 = 0, vy = 0, vy1 = 0, vy2 = 0;
-#pragma unroll
-            for (int a = 0; a < 8; ++a) {
-                if (a == nx) { vx = hx.v[a]; vx1 = hx.d1[a]; vx2 = hx.d2[a]; }
-                if (a == ny) { vy = hy.v[a]; vy1 = hy.d1[a]; vy2 = hy.d2[a]; }
-            }
+            const Herm1D hx = hermite_1d(z[0], nx), hy = hermite_1d(z[1], ny);
+            const double vx = hx.v, vx1 = hx.d1, vx2 = hx.d2, vy = hy.v, vy1 = hy.d1, vy2 = hy.d2;
             double* S = sptr(w);
             S[blk.aug() + i * 2 * ns + k] = inv_sqrt_pi * vx * vy;
             S[blk.aug() + i * 2 * ns + ns + k] = (i == k) ? 1.0 : 0.0;

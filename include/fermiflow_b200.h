@@ -104,6 +104,8 @@ int ff_occupation_sample(const double* logits, int S, const double* uniforms, lo
 /* Raw FP64 FMA throughput of the device (roofline denominator): runs `iters` dependent
  * DFMA chains on every SM and returns the achieved FLOP/s in *flops_host. */
 int ff_fp64_peak(int iters, double* flops_host, void* stream);
+/* Same for the FP64 tensor-core path (mma.sync m8n8k4 f64, "DMMA"). */
+int ff_fp64_mma_peak(int iters, double* flops_host, void* stream);
 
 #ifdef __cplusplus
 }
