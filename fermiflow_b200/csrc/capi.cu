@@ -32,7 +32,7 @@ int cuda_fail(cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
-struct DevInfo { int sms = 0; int smem_optin = 0; bool ok = false; };
+struct DevInfo { int sms = 0; int smem_optin = 0; int smem_sm = 0; int smem_reserved = 1024; bool ok = false; };
 DevInfo dev_info() {
     static thread_local DevInfo di[16];
     int dev = 0;
@@ -41,6 +41,8 @@ DevInfo dev_info() {
     if (!d.ok) {
         cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&d.smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        cudaDeviceGetAttribute(&d.smem_reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev);
         d.ok = true;
     }
     return d;
@@ -91,8 +93,14 @@ int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t
     }
     int common = 64 + 6 * (even(m->H_eta) + even(m->H_mu));
     common = even(common) + 2 * ((a.NP + 7) / 8) + 2;
-    const long long budget = (long long)di.smem_optin / 8 - common;
-    const int target_threads = eloc ? 512 : 256;
+    // E_loc sweep: aim for two resident CTAs per SM (their FP64-bound and shared-memory-bound
+    // phases overlap), fall back to one large CTA when a walker does not fit in half an SM.
+    long long budget = (long long)di.smem_optin / 8 - common;
+    int target_threads = eloc ? 512 : 256;
+    if (eloc) {
+        const long long half = ((long long)di.smem_sm / 2 - di.smem_reserved) / 8 - common;
+        if (half >= a.wstride && a.P <= 256) { budget = half; target_threads = 256; }
+    }
     int W = (int)(budget / a.wstride);
     if (W > target_threads / a.P) W = target_threads / a.P;
     if (a.P > 512) return fail(-2, "n = %d needs %d threads per walker (> 512)", n, a.P);

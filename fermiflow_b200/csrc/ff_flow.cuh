@@ -13,6 +13,13 @@
 
 namespace ff {
 
+#ifdef FF_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define FF_TICK(k) do { if (MODE == MODE_ELOC && tid == 0) { long long now_ = clock64(); tacc[k] += now_ - tlast; tlast = now_; } } while (0)
+#else
+#define FF_TICK(k) do {} while (0)
+#endif
+
 enum FlowMode { MODE_V = 0, MODE_DIV = 1, MODE_STASH = 2, MODE_ELOC = 3 };
 
 struct FlowArgs {
@@ -167,24 +174,61 @@ __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
     __syncthreads();
 }
 
-// Gram matrix M = J J^T of every walker on the FP64 tensor cores: upper block triangle of
-// 8x8 blocks, one warp per block, K loop of D8/4 DMMAs.  J: [D8][DP] (rows >= D zero).
+// ---- FP64 tensor-core (DMMA m8n8k4) building blocks --------------------------------------
+// A dependent DMMA chain issues only every ~150 cycles, so every warp task below carries
+// up to 2*CH independent accumulators (CH column blocks x two interleaved halves of K).
+constexpr int kCH = 5;
+
+// C[c] (8x8 each, c < nch) = A(8 x K) * B_c(K x 8).  Lane (g = lane/4, t = lane%4):
+//   a_of(k)    -> A[g][k + t]          (the caller bakes g, t into the functor)
+//   b_of(c, k) -> B_c[k + t][g]
+// K is a multiple of 4.  Results: acc[c][0..1] = C_c[g][2t, 2t+1].
+template <class AF, class BF>
+__device__ __forceinline__ void dmma_chunk(int K, int nch, AF a_of, BF b_of, double (&acc)[kCH][2]) {
+    double e[kCH][2], o[kCH][2];
+#pragma unroll
+    for (int c = 0; c < kCH; ++c) { e[c][0] = e[c][1] = o[c][0] = o[c][1] = 0.0; }
+    int k = 0;
+    for (; k + 8 <= K; k += 8) {
+        const double a0 = a_of(k), a1 = a_of(k + 4);
+#pragma unroll
+        for (int c = 0; c < kCH; ++c)
+            if (c < nch) {
+                dmma_m8n8k4(e[c][0], e[c][1], a0, b_of(c, k));
+                dmma_m8n8k4(o[c][0], o[c][1], a1, b_of(c, k + 4));
+            }
+    }
+    if (k < K) {
+        const double a0 = a_of(k);
+#pragma unroll
+        for (int c = 0; c < kCH; ++c)
+            if (c < nch) dmma_m8n8k4(e[c][0], e[c][1], a0, b_of(c, k));
+    }
+#pragma unroll
+    for (int c = 0; c < kCH; ++c) { acc[c][0] = e[c][0] + o[c][0]; acc[c][1] = e[c][1] + o[c][1]; }
+}
+
+// Gram matrix M = J J^T (upper block triangle of 8x8 blocks) of every walker.  A task is a
+// run of up to kCH consecutive column blocks of one block row.  J: [D8][DP], rows >= D zero.
 __device__ __forceinline__ void gram_dmma(int W, int D8, int DP, double* wbase, int wstride, int oJ, int off_AM) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    const int g = lane >> 2, t = lane & 3, NB = D8 >> 3, ntri = NB * (NB + 1) / 2;
-    for (int task = warp; task < W * ntri; task += nwarp) {
-        const int w = task / ntri;
-        int rem = task - w * ntri, rb = 0;
-        while (rem >= NB - rb) { rem -= NB - rb; ++rb; }
-        const int cb = rb + rem;
+    const int g = lane >> 2, t = lane & 3, NB = D8 >> 3;
+    int tpw = 0;                                   // tasks per walker
+    for (int rb = 0; rb < NB; ++rb) tpw += (NB - rb + kCH - 1) / kCH;
+    for (int task = warp; task < W * tpw; task += nwarp) {
+        const int w = task / tpw;
+        int rem = task - w * tpw, rb = 0;
+        for (;; ++rb) { const int c = (NB - rb + kCH - 1) / kCH; if (rem < c) break; rem -= c; }
+        const int cb0 = rb + rem * kCH, nch = min(kCH, NB - cb0);
         const double* J = wbase + (size_t)w * wstride + oJ;
         const double* A = J + (8 * rb + g) * DP + t;
-        const double* B = J + (8 * cb + g) * DP + t;
-        double c0 = 0.0, c1 = 0.0;
-#pragma unroll 2
-        for (int k = 0; k < D8; k += 4) dmma_m8n8k4(c0, c1, A[k], B[k]);
-        double* M = wbase + (size_t)w * wstride + off_AM + (8 * rb + g) * DP + 8 * cb + 2 * t;
-        *reinterpret_cast<double2*>(M) = make_double2(c0, c1);
+        const double* B = J + (8 * cb0 + g) * DP + t;
+        double acc[kCH][2];
+        dmma_chunk(D8, nch, [&](int k) { return A[k]; }, [&](int c, int k) { return B[c * 8 * DP + k]; }, acc);
+        double* M = wbase + (size_t)w * wstride + off_AM + (8 * rb + g) * DP + 8 * cb0 + 2 * t;
+#pragma unroll
+        for (int c = 0; c < kCH; ++c)
+            if (c < nch) *reinterpret_cast<double2*>(M + 8 * c) = make_double2(acc[c][0], acc[c][1]);
     }
 }
 
@@ -260,8 +304,12 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
         }
         __syncthreads();
 
+#ifdef FF_PHASE_TIMING
+        long long tacc[16] = {0}; long long tlast = clock64();
+#endif
         for (int stage = 0; stage < NS; ++stage) {
             const int sub = stage & 3;
+            FF_TICK(0);
             // ======== S0: per-item radial functions (+ Gram matrix for ELOC) ==============
             double rx = 0, ry = 0, ca = 0, cb = 0, ccq = 0, ceq = 0, cf = 0;
             if (it_valid) {
@@ -313,9 +361,12 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                             a.stash_y[(b * NS + stage) * D + e] = (wbase + (size_t)w * wstride)[e];
                 }
             }
+            FF_TICK(1);
             if (MODE == MODE_ELOC) {
                 gram_dmma(W, D8, DP, wbase, wstride, oJ, a.off_AM);
+                FF_TICK(2);
                 __syncthreads();
+                FF_TICK(3);
                 // ======== S1: second-derivative contractions per item ====================
                 if (it_valid) {
                     const double* M = myS + a.off_AM;
@@ -336,7 +387,9 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                     G[7] = fma(ccq, trw, ceq * rwr);
                 }
             }
+            FF_TICK(4);
             __syncthreads();
+            FF_TICK(5);
             // ======== S2: gather per particle, build Jacobian matrix ======================
             {
                 constexpr int NC = (MODE == MODE_ELOC) ? kGRec : (MODE >= MODE_DIV ? 3 : 2);
@@ -346,15 +399,29 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                     for (int g = tid; g < n * NC; g += T) {
                         const int i = g / NC, cc = g - i * NC;
                         const int c = (MODE == MODE_ELOC) ? cc : (cc == 2 ? 6 : cc);
-                        double accm = 0.0, accp = 0.0;
+                        double accm = 0.0, accp = 0.0, accm2 = 0.0, accp2 = 0.0;
                         {   // pairs (j, i), j < i : stored with r = y_j - y_i
                             int idx = i - 1;                       // pair_index(0, i)
-                            for (int j = 0; j < i; ++j) { accm += G[idx * kGRec + c]; idx += n - j - 2; }
+                            int j = 0;
+                            for (; j + 2 <= i; j += 2) {
+                                const int idx2 = idx + n - j - 2;
+                                const double v0 = G[idx * kGRec + c], v1 = G[idx2 * kGRec + c];
+                                accm += v0; accm2 += v1;
+                                idx = idx2 + n - j - 3;
+                            }
+                            if (j < i) accm += G[idx * kGRec + c];
                         }
                         {   // pairs (i, j), j > i : consecutive
                             const double* Gi = G + pair_index(i, i + 1, n) * kGRec + c;
-                            for (int j = i + 1; j < n; ++j) { accp += *Gi; Gi += kGRec; }
+                            int j = i + 1;
+                            for (; j + 4 <= n; j += 4) {
+                                const double v0 = Gi[0], v1 = Gi[kGRec], v2 = Gi[2 * kGRec], v3 = Gi[3 * kGRec];
+                                accp += v0; accp2 += v1; accp += v2; accp2 += v3;
+                                Gi += 4 * kGRec;
+                            }
+                            for (; j < n; ++j) { accp += *Gi; Gi += kGRec; }
                         }
+                        accm += accm2; accp += accp2;
                         double acc = (c < 6) ? accp - accm : accp + accm;
                         if (c == 6 || c == 7) acc *= 0.5;
                         if (has_mu) acc += G[(NP + i) * kGRec + c];
@@ -380,52 +447,63 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                     A[(j2 + 1) * DP + i2] = a01; A[(j2 + 1) * DP + i2 + 1] = a11;
                 }
             }
+            FF_TICK(6);
             __syncthreads();
+            FF_TICK(7);
             // ======== S3: derivative of the whole state ===================================
             if (MODE == MODE_ELOC) {
-                // K.J = A * J on the FP64 tensor cores: one warp per 8x8 output block
+                // K.J = A J, K.L = A L + kLx, K.gD = -(u^T J) on the FP64 tensor cores.  Tasks
+                // per walker: NB block rows of K.J (chunks of kCH column blocks) and two
+                // "row vector x matrix" products (L^T A, A symmetric; u^T J).
                 {
                     const int g = lane >> 2, t = lane & 3, NB = D8 >> 3;
-                    for (int task = warp; task < W * NB * NB; task += nwarp) {
-                        const int w = task / (NB * NB), rem = task - w * NB * NB;
-                        const int rb = rem / NB, cbk = rem - rb * NB;
+                    const int nchunk = (NB + kCH - 1) / kCH;
+                    const int tpw = NB * nchunk + 2 * nchunk;
+                    for (int task = warp; task < W * tpw; task += nwarp) {
+                        const int w = task / tpw;
+                        int rem = task - w * tpw;
                         double* Sw = wbase + (size_t)w * wstride;
-                        const double* Ap = Sw + a.off_AM + (8 * rb + g) * DP + t;     // A[row][k]
-                        const double* Bp = Sw + oJ + t * DP + 8 * cbk + g;            // J[k][col]
-                        double c0 = 0.0, c1 = 0.0;
-#pragma unroll 2
-                        for (int k = 0; k < D8; k += 4) dmma_m8n8k4(c0, c1, Ap[k], Bp[k * DP]);
-                        double* K = Sw + oK + oJ + (8 * rb + g) * DP + 8 * cbk + 2 * t;
-                        *reinterpret_cast<double2*>(K) = make_double2(c0, c1);
-                    }
-                }
-                // K.L = A L + kLx ;  K.gD = -(u^T J)
-                for (int w = 0; w < W; ++w) {
-                    double* Sw = wbase + (size_t)w * wstride;
-                    for (int e = tid; e < 2 * D; e += T) {
-                        if (e < D) {
-                            const double* A = Sw + a.off_AM + e * DP;
-                            const double* L = Sw + oL;
-                            double acc0 = (Sw + a.off_kLx)[e], acc1 = 0.0;
-                            for (int k = 0; k < D; k += 2) {
-                                const double2 av = *reinterpret_cast<const double2*>(A + k);
-                                const double2 lv = *reinterpret_cast<const double2*>(L + k);
-                                acc0 = fma(av.x, lv.x, acc0); acc1 = fma(av.y, lv.y, acc1);
-                            }
-                            (Sw + oK)[oL + e] = acc0 + acc1;
+                        const double* Amat = Sw + a.off_AM;
+                        const double* Jmat = Sw + oJ;
+                        double acc[kCH][2];
+                        if (rem < NB * nchunk) {
+                            const int rb = rem / nchunk, ch = rem - rb * nchunk;
+                            const int cb0 = ch * kCH, nch = min(kCH, NB - cb0);
+                            const double* Ap = Amat + (8 * rb + g) * DP + t;           // A[row][k]
+                            const double* Bp = Jmat + t * DP + 8 * cb0 + g;            // J[k][col]
+                            dmma_chunk(D8, nch, [&](int k) { return Ap[k]; },
+                                       [&](int c, int k) { return Bp[k * DP + 8 * c]; }, acc);
+                            double* K = Sw + oK + oJ + (8 * rb + g) * DP + 8 * cb0 + 2 * t;
+#pragma unroll
+                            for (int c = 0; c < kCH; ++c)
+                                if (c < nch) *reinterpret_cast<double2*>(K + 8 * c) = make_double2(acc[c][0], acc[c][1]);
                         } else {
-                            const int c = e - D;
-                            const double* u = Sw + a.off_u;
-                            const double* J = Sw + oJ + c;
-                            double acc0 = 0.0, acc1 = 0.0;
-                            for (int k = 0; k < D; k += 2) {
-                                acc0 = fma(u[k], J[k * DP], acc0);
-                                acc1 = fma(u[k + 1], J[(k + 1) * DP], acc1);
+                            rem -= NB * nchunk;
+                            const bool isL = rem < nchunk;                 // L^T A  or  u^T J
+                            const int ch = isL ? rem : rem - nchunk;
+                            const int cb0 = ch * kCH, nch = min(kCH, NB - cb0);
+                            const double* vec = isL ? Sw + oL : Sw + a.off_u;
+                            const double* Bp = (isL ? Amat : Jmat) + t * DP + 8 * cb0 + g;
+                            dmma_chunk(D8, nch, [&](int k) { return (g == 0 && k + t < D) ? vec[k + t] : 0.0; },
+                                       [&](int c, int k) { return Bp[k * DP + 8 * c]; }, acc);
+                            if (g == 0) {
+#pragma unroll
+                                for (int c = 0; c < kCH; ++c)
+                                    if (c < nch) {
+#pragma unroll
+                                        for (int q = 0; q < 2; ++q) {
+                                            const int col = 8 * (cb0 + c) + 2 * t + q;
+                                            if (col < D) {
+                                                if (isL) (Sw + oK)[oL + col] = acc[c][q] + (Sw + a.off_kLx)[col];
+                                                else (Sw + oK)[oG + col] = -acc[c][q];
+                                            }
+                                        }
+                                    }
                             }
-                            (Sw + oK)[oG + c] = -(acc0 + acc1);
                         }
                     }
                 }
+                FF_TICK(8);
                 // scalar rates: one warp per walker, shuffle reductions
                 for (int w = nwarp - 1 - warp; w < W && w >= 0; w += nwarp) {
                     double* Sw = wbase + (size_t)w * wstride;
@@ -450,32 +528,70 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                     (Sw + oK)[oDelta] = -rho;
                 }
             }
+            FF_TICK(9);
             __syncthreads();
+            FF_TICK(10);
             // ======== S4: 3/8-rule RK4 bookkeeping (torchdiffeq rk4_alt_step_func) ========
             for (int w = 0; w < W; ++w) {
                 double* Sw = wbase + (size_t)w * wstride;
-                for (int e = tid; e < NSV; e += T) {
-                    const double k = Sw[oK + e] * h;
-                    if (sub == 0) {
-                        const double y0 = Sw[e];
-                        Sw[oP3 + e] = fma(k, -1.0 / 3.0, y0);
-                        Sw[oP4 + e] = y0 + k;
-                        Sw[oPO + e] = fma(k, 0.125, y0);
-                        Sw[e] = fma(k, 1.0 / 3.0, y0);
-                    } else if (sub == 1) {
-                        Sw[e] = Sw[oP3 + e] + k;
-                        Sw[oP4 + e] -= k;
-                        Sw[oPO + e] = fma(k, 0.375, Sw[oPO + e]);
-                    } else if (sub == 2) {
-                        Sw[e] = Sw[oP4 + e] + k;
-                        Sw[oPO + e] = fma(k, 0.375, Sw[oPO + e]);
-                    } else {
-                        Sw[e] = fma(k, 0.125, Sw[oPO + e]);
+                if ((NSV & 1) == 0) {
+                    // two elements per thread, 128-bit shared-memory accesses
+                    double2* S2 = reinterpret_cast<double2*>(Sw);
+                    double2* P32 = reinterpret_cast<double2*>(Sw + oP3);
+                    double2* P42 = reinterpret_cast<double2*>(Sw + oP4);
+                    double2* PO2 = reinterpret_cast<double2*>(Sw + oPO);
+                    const double2* K2 = reinterpret_cast<const double2*>(Sw + oK);
+                    for (int e = tid; e < NSV / 2; e += T) {
+                        double2 k = K2[e]; k.x *= h; k.y *= h;
+                        if (sub == 0) {
+                            const double2 y0 = S2[e];
+                            P32[e] = make_double2(fma(k.x, -1.0 / 3.0, y0.x), fma(k.y, -1.0 / 3.0, y0.y));
+                            P42[e] = make_double2(y0.x + k.x, y0.y + k.y);
+                            PO2[e] = make_double2(fma(k.x, 0.125, y0.x), fma(k.y, 0.125, y0.y));
+                            S2[e] = make_double2(fma(k.x, 1.0 / 3.0, y0.x), fma(k.y, 1.0 / 3.0, y0.y));
+                        } else if (sub == 1) {
+                            const double2 p3 = P32[e], p4 = P42[e], po = PO2[e];
+                            S2[e] = make_double2(p3.x + k.x, p3.y + k.y);
+                            P42[e] = make_double2(p4.x - k.x, p4.y - k.y);
+                            PO2[e] = make_double2(fma(k.x, 0.375, po.x), fma(k.y, 0.375, po.y));
+                        } else if (sub == 2) {
+                            const double2 p4 = P42[e], po = PO2[e];
+                            S2[e] = make_double2(p4.x + k.x, p4.y + k.y);
+                            PO2[e] = make_double2(fma(k.x, 0.375, po.x), fma(k.y, 0.375, po.y));
+                        } else {
+                            const double2 po = PO2[e];
+                            S2[e] = make_double2(fma(k.x, 0.125, po.x), fma(k.y, 0.125, po.y));
+                        }
+                    }
+                } else {
+                    for (int e = tid; e < NSV; e += T) {
+                        const double k = Sw[oK + e] * h;
+                        if (sub == 0) {
+                            const double y0 = Sw[e];
+                            Sw[oP3 + e] = fma(k, -1.0 / 3.0, y0);
+                            Sw[oP4 + e] = y0 + k;
+                            Sw[oPO + e] = fma(k, 0.125, y0);
+                            Sw[e] = fma(k, 1.0 / 3.0, y0);
+                        } else if (sub == 1) {
+                            Sw[e] = Sw[oP3 + e] + k;
+                            Sw[oP4 + e] -= k;
+                            Sw[oPO + e] = fma(k, 0.375, Sw[oPO + e]);
+                        } else if (sub == 2) {
+                            Sw[e] = Sw[oP4 + e] + k;
+                            Sw[oPO + e] = fma(k, 0.375, Sw[oPO + e]);
+                        } else {
+                            Sw[e] = fma(k, 0.125, Sw[oPO + e]);
+                        }
                     }
                 }
             }
+            FF_TICK(11);
             __syncthreads();
+            FF_TICK(12);
         }   // stages
+#ifdef FF_PHASE_TIMING
+        if (MODE == MODE_ELOC && tid == 0) for (int k = 0; k < 16; ++k) atomicAdd(&g_phase_cycles[k], (unsigned long long)tacc[k]);
+#endif
 
         // ---- outputs ----------------------------------------------------------------------
         for (int w = 0; w < W; ++w) {
