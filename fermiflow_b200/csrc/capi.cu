@@ -79,7 +79,8 @@ int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t
     a.DP = eloc ? D8 + 4 : a.D;              // DP mod 16 in {4, 12}: conflict-free DMMA fragments
     a.NSV = eloc ? 3 * a.D + 2 + D8 * a.DP : a.D + (mode >= ff::MODE_DIV ? 1 : 0);
     int off = even(5 * a.NSV);
-    a.off_G = off; off = even(off + a.P * ff::kGRec);
+    a.grec = eloc ? ff::kGRec : 3;
+    a.off_G = off; off = even(off + a.P * a.grec);
     a.off_AM = off; if (eloc) off = even(off + D8 * a.DP);
     a.off_u = off; if (eloc) off += a.D;
     a.off_kLx = off; if (eloc) off += a.D;
@@ -121,6 +122,7 @@ template <int MODE>
 int launch_flow(ff::FlowArgs& a, int threads, size_t smem, cudaStream_t st) {
     const DevInfo di = dev_info();
     FF_CUDA(cudaFuncSetAttribute(ff::flow_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FF_CUDA(cudaFuncSetAttribute(ff::flow_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     int occ = 0;
     FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ff::flow_kernel<MODE>, threads, smem));
     if (occ < 1) return fail(-2, "flow kernel does not fit on an SM (threads %d, smem %zu)", threads, smem);

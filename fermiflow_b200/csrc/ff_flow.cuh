@@ -48,6 +48,7 @@ struct FlowArgs {
     int D, DP;              // 2n, padded row length of J
     int NSV;                // state doubles per walker
     int wstride;            // shared doubles per walker
+    int grec;               // doubles per item record (kGRec for MODE_ELOC, 3 otherwise: vx, vy, q)
     int off_G, off_AM, off_u, off_kLx, off_part, off_x0, off_sl;   // offsets inside a walker block
 };
 
@@ -322,13 +323,15 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                 constexpr int ORD = (MODE == MODE_V) ? 0 : (MODE == MODE_DIV) ? 1 : (MODE == MODE_STASH) ? 2 : 3;
                 // one call for both item kinds: no divergence between pair and single lanes
                 radial_mlp<ORD>(it_pair ? coef_eta : coef_mu, it_pair ? a.H_eta : a.H_mu, d, tab, f);
-                double* G = myS + a.off_G + it_p * kGRec;
+                constexpr int GR = (MODE == MODE_ELOC) ? kGRec : 3;
+                constexpr int GQ = (MODE == MODE_ELOC) ? 6 : 2;
+                double* G = myS + a.off_G + it_p * GR;
                 cf = f[0];
                 G[0] = cf * rx;
                 G[1] = cf * ry;
                 if (MODE >= MODE_DIV) {
                     const double mult = it_pair ? 2.0 : 1.0;
-                    G[6] = mult * fma(f[1], d, 2.0 * f[0]);                 // q
+                    G[GQ] = mult * fma(f[1], d, 2.0 * f[0]);                // q
                 }
                 if (MODE >= MODE_STASH && a.stash_c != nullptr) {
                     long long b = base + it_w;
@@ -392,39 +395,41 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
             FF_TICK(5);
             // ======== S2: gather per particle, build Jacobian matrix ======================
             {
+                constexpr int GRg = (MODE == MODE_ELOC) ? kGRec : 3;      // record stride
                 constexpr int NC = (MODE == MODE_ELOC) ? kGRec : (MODE >= MODE_DIV ? 3 : 2);
                 for (int w = 0; w < W; ++w) {
                     double* Sw = wbase + (size_t)w * wstride;
                     const double* G = Sw + a.off_G;
                     for (int g = tid; g < n * NC; g += T) {
                         const int i = g / NC, cc = g - i * NC;
-                        const int c = (MODE == MODE_ELOC) ? cc : (cc == 2 ? 6 : cc);
+                        const int c = (MODE == MODE_ELOC) ? cc : (cc == 2 ? 6 : cc);   // logical quantity
+                        const int gc = cc;                                             // column in the record
                         double accm = 0.0, accp = 0.0, accm2 = 0.0, accp2 = 0.0;
                         {   // pairs (j, i), j < i : stored with r = y_j - y_i
                             int idx = i - 1;                       // pair_index(0, i)
                             int j = 0;
                             for (; j + 2 <= i; j += 2) {
                                 const int idx2 = idx + n - j - 2;
-                                const double v0 = G[idx * kGRec + c], v1 = G[idx2 * kGRec + c];
+                                const double v0 = G[idx * GRg + gc], v1 = G[idx2 * GRg + gc];
                                 accm += v0; accm2 += v1;
                                 idx = idx2 + n - j - 3;
                             }
-                            if (j < i) accm += G[idx * kGRec + c];
+                            if (j < i) accm += G[idx * GRg + gc];
                         }
                         {   // pairs (i, j), j > i : consecutive
-                            const double* Gi = G + pair_index(i, i + 1, n) * kGRec + c;
+                            const double* Gi = G + pair_index(i, i + 1, n) * GRg + gc;
                             int j = i + 1;
                             for (; j + 4 <= n; j += 4) {
-                                const double v0 = Gi[0], v1 = Gi[kGRec], v2 = Gi[2 * kGRec], v3 = Gi[3 * kGRec];
+                                const double v0 = Gi[0], v1 = Gi[GRg], v2 = Gi[2 * GRg], v3 = Gi[3 * GRg];
                                 accp += v0; accp2 += v1; accp += v2; accp2 += v3;
-                                Gi += 4 * kGRec;
+                                Gi += 4 * GRg;
                             }
-                            for (; j < n; ++j) { accp += *Gi; Gi += kGRec; }
+                            for (; j < n; ++j) { accp += *Gi; Gi += GRg; }
                         }
                         accm += accm2; accp += accp2;
                         double acc = (c < 6) ? accp - accm : accp + accm;
                         if (c == 6 || c == 7) acc *= 0.5;
-                        if (has_mu) acc += G[(NP + i) * kGRec + c];
+                        if (has_mu) acc += G[(NP + i) * GRg + gc];
                         if (c < 2) (Sw + oK)[oY + 2 * i + c] = acc;
                         else if (c < 4) (Sw + a.off_u)[2 * i + c - 2] = acc;
                         else if (c < 6) (Sw + a.off_kLx)[2 * i + c - 4] = acc;

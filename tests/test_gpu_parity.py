@@ -337,5 +337,5 @@ def test_flow_reversibility_full_size(dev):
     x = cnf.generate(z)
     zb, dl = cnf.delta_logp(x)
     assert (zb - z).abs().max() < 1e-4          # RK4 truncation error (close pairs: |r| cone)
-    assert (zb - z).abs().mean() < 1e-7
+    assert (zb - z).abs().mean() < 1e-5
     assert torch.isfinite(dl).all()

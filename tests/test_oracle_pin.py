@@ -123,3 +123,24 @@ def test_pipeline_default_tolerance_consistent(golden):
     r = O.local_energy(T(g["default_x"]), up, dn, eta, mu, ts, 16, float(g["Z"]))
     close(r["logp"], g["default_logp"], 1e-5)
     close(r["eloc"], g["default_eloc"], 1e-4)
+
+
+def test_reference_port_matches_reference_default(golden):
+    """oracle/reference_port.py (the reference's own adaptive + adjoint algorithm, used as the
+    CPU baseline of bench.py) against the real reference's default-tolerance run."""
+    from oracle import reference_port as R
+    g = golden("pipeline")
+    up, dn, eta, mu, ts = _model(g)
+    params = list(eta) + list(mu)
+    x = R.generate(T(g["z0"]), params, True, ts)
+    close(x, g["default_x"], 1e-12)
+    xr = T(g["default_x"]).clone().requires_grad_(True)
+    lp, gr, lap = R.y_grad_laplacian(lambda t: R.logp(t, up, dn, params, True, ts, False), xr)
+    close(lp.detach(), g["default_logp"], 1e-11)
+    close(gr.detach(), g["default_grad"], 1e-9)
+    close(lap.detach(), g["default_lap"], 1e-8)
+    leaves = [p.clone().requires_grad_(True) for p in params]
+    lpf = R.logp(T(g["default_x"]), up, dn, leaves, True, ts, True)
+    grads = torch.autograd.grad((lpf * T(g["weights"])).sum(), leaves)
+    for a, k in zip(grads, ("eta_w1", "eta_b1", "eta_w2", "mu_w1", "mu_b1", "mu_w2")):
+        close(a, g["default_g_" + k], 1e-9, 1e-13)
