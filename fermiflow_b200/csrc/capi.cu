@@ -77,8 +77,11 @@ int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t
     const bool eloc = mode == ff::MODE_ELOC;
     const int D8 = (a.D + 7) & ~7;
     a.DP = eloc ? D8 + 4 : a.D;              // DP mod 16 in {4, 12}: conflict-free DMMA fragments
-    a.NSV = eloc ? 3 * a.D + 2 + D8 * a.DP : a.D + (mode >= ff::MODE_DIV ? 1 : 0);
-    int off = even(5 * a.NSV);
+    a.NV = eloc ? 3 * a.D + 2 : a.D + (mode >= ff::MODE_DIV ? 1 : 0);
+    a.NSV = eloc ? a.NV + D8 * a.DP : a.NV;
+    a.NPAR = eloc ? a.NV + a.D * a.D : a.NV;
+    if (eloc) { a.NSV = even(a.NSV); a.NPAR = even(a.NPAR); }
+    int off = even(a.NSV + 4 * a.NPAR);
     a.grec = eloc ? ff::kGRec : 3;
     a.off_G = off; off = even(off + a.P * a.grec);
     a.off_AM = off; if (eloc) off = even(off + D8 * a.DP);
@@ -90,9 +93,9 @@ int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t
     a.wstride = even(off);
     if (eloc) {
         const int need = ff::slater_scratch_size(m->n_up, m->n_dn) + 2 * a.D + n * n + a.NP + 8;
-        if (need > 4 * a.NSV) return fail(-2, "internal: finale scratch does not fit");
+        if (need > 4 * a.NPAR) return fail(-2, "internal: finale scratch does not fit");
     }
-    int common = 64 + 6 * (even(m->H_eta) + even(m->H_mu));
+    int common = ff::kTabDoubles + 6 * (even(m->H_eta) + even(m->H_mu));
     common = even(common) + 2 * ((a.NP + 7) / 8) + 2;
     // E_loc sweep: aim for two resident CTAs per SM (their FP64-bound and shared-memory-bound
     // phases overlap), fall back to one large CTA when a walker does not fit in half an SM.

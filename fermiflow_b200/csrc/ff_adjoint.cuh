@@ -153,14 +153,15 @@ __global__ void __launch_bounds__(512) pgrad_kernel(const PGradArgs a) {
     const int tid = threadIdx.x, T = blockDim.x;
     const int n = a.n, D = a.D, NP = a.NP, R = a.R;
     const int NS = 4 * a.nsteps;
-    double* tab = smem;                                  // 64
-    double* rec = tab + 64;                              // R x 2D   (y, kbar)
+    double* tab = smem;                                  // kTabDoubles
+    double* rec = tab + kTabDoubles;                     // R x 2D   (y, kbar)
     double* kdl = rec + (size_t)R * 2 * D;               // R
     double* it_e = kdl + ((R + 1) & ~1);                 // R*NP x 4  (d, A, Bc, -)
     double* it_m = it_e + (size_t)R * NP * 4;            // R*n x 4
     unsigned char* pair_i = reinterpret_cast<unsigned char*>(it_m + (size_t)R * n * 4);
     unsigned char* pair_j = pair_i + ((NP + 7) & ~7);
-    for (int i = tid; i < 64; i += T) tab[i] = c_exp2_64[i];
+    fill_exp_table(tab);
+    const double* tabl = tab + (tid & 15);
     for (int p = tid; p < NP; p += T) {
         int i = 0, rem = p;
         while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(512) pgrad_kernel(const PGradArgs a) {
                 const double2 dA = *reinterpret_cast<const double2*>(items + 4 * it);
                 const double Bc = items[4 * it + 2];
                 const double d = dA.x, A = dA.y;
-                const double s = sigmoid_fast(fma(w1, d, b1), tab);
+                const double s = sigmoid_fast(fma(w1, d, b1), tabl);
                 const double s1 = fma(-s, s, s);
                 const double s2 = s1 * fma(-2.0, s, 1.0);
                 const double Bw = Bc * w1;

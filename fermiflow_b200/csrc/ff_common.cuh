@@ -8,81 +8,54 @@ namespace ff {
 constexpr int kMaxOrb = 36;      // HO2D exposes 36 orbitals (orbitals.py:89, shells 0..7)
 constexpr int kGRec = 11;        // per-item gather record length (odd: bank-conflict free)
 
-// 2^(j/64), j = 0..63 (correctly rounded); copied to shared memory by every kernel that
-// evaluates the backflow MLPs.
-__constant__ double c_exp2_64[64] = {
+// 2^(j/32), j = 0..31 (correctly rounded).  Every kernel that evaluates the backflow MLPs
+// keeps a shared-memory copy replicated 16 times (entry j of lane l at tab[16 j + (l & 15)]),
+// so that the per-lane table look-up of the exponential is bank-conflict free.
+constexpr int kTabDoubles = 512;
+__constant__ double c_exp2_32[32] = {
     1.0,
-    1.0108892860517005,
     1.0218971486541166,
-    1.0330248790212284,
     1.0442737824274138,
-    1.0556451783605572,
     1.0671404006768237,
-    1.0787607977571199,
     1.0905077326652577,
-    1.102382583307841,
     1.1143867425958924,
-    1.1265216186082418,
     1.1387886347566916,
-    1.1511892299529827,
     1.1637248587775775,
-    1.1763969916502812,
     1.189207115002721,
-    1.202156731452703,
     1.215247359980469,
-    1.22848053610687,
     1.241857812073484,
-    1.255380757024691,
     1.2690509571917332,
-    1.2828700160787783,
     1.2968395546510096,
-    1.3109612115247644,
     1.3252366431597413,
-    1.339667524053303,
     1.3542555469368927,
-    1.3690024229745905,
     1.383909881963832,
-    1.3989796725383112,
     1.4142135623730951,
-    1.42961333839197,
     1.4451808069770467,
-    1.460917794180647,
     1.4768261459394993,
-    1.4929077282912648,
     1.5091644275934228,
-    1.5255981507445384,
     1.5422108254079407,
-    1.559004400237837,
     1.5759808451078865,
-    1.593142151342267,
     1.6104903319492543,
-    1.6280274218573478,
     1.645755478153965,
-    1.6636765803267364,
     1.681792830507429,
-    1.7001063537185235,
     1.718619298122478,
-    1.7373338352737062,
     1.7562521603732995,
-    1.7753764925265212,
     1.7947090750031072,
-    1.8142521755003989,
     1.8340080864093424,
-    1.8539791250833855,
     1.8741676341103,
-    1.8945759815869656,
     1.9152065613971474,
-    1.9360617934922943,
-    1.9571441241754002,
-    1.978456026387951
+    1.9571441241754002
 };
+__device__ __forceinline__ void fill_exp_table(double* tab) {
+    for (int i = threadIdx.x; i < kTabDoubles; i += blockDim.x) tab[i] = c_exp2_32[i >> 4];
+}
 
 // exp() range-reduction constants, read through the constant bank so that ptxas folds them
 // into DFMA operands instead of re-materialising 64-bit immediates inside the hot loop.
-__constant__ double c_sig[8] = {92.33248261689366,        // 64 / ln 2
-                                0.01083042469326756,      // ln2/64, low 21 mantissa bits zero
-                                2.9815858269852933e-12,   // ln2/64 remainder
-                                1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.0, 0.0};
+__constant__ double c_sig[8] = {46.16624130844683,        // 32 / ln 2
+                                0.02166084938653512,      // ln2/32, low 21 mantissa bits zero
+                                5.9631716539705866e-12,   // ln2/32 remainder
+                                1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.0};
 
 __device__ __forceinline__ double rcp_approx(double x) {
     double y;
@@ -90,31 +63,29 @@ __device__ __forceinline__ double rcp_approx(double x) {
     return y;
 }
 
-// Logistic sigmoid 1 / (1 + exp(-u)) in fp64 with 14 FP64-pipe instructions:
-//   exp(-u) = 2^m * 2^(j/64) * exp(r), |r| <= ln2/128, degree-5 Taylor (remainder 3.5e-17),
-//   reciprocal = MUFU seed + one cubic Newton step.
-// `tab` is the shared-memory copy of c_exp2_64.  Valid for |u| < 2^24 (saturates correctly
-// for |u| > 709); relative error a few ulp.  Matches torch.sigmoid (MLP.py:17) to ~4e-16.
-__device__ __forceinline__ double sigmoid_fast(double u, const double* __restrict__ tab) {
-    const double L = 92.33248261689366;                 // 64 / ln 2
+// Logistic sigmoid 1 / (1 + exp(-u)) in fp64 with 15 FP64-pipe instructions:
+//   exp(-u) = 2^m * 2^(j/32) * exp(r), |r| <= ln2/64, degree-6 Taylor (remainder 3.5e-18),
+//   reciprocal = MUFU.RCP64H seed + one cubic Newton step.
+// `tabl` = shared exp table + (lane & 15).  Valid for |u| < 2^25 (saturates correctly for
+// |u| > 709); relative error a few ulp.  Matches torch.sigmoid (MLP.py:17) to ~4e-16.
+__device__ __forceinline__ double sigmoid_fast(double u, const double* __restrict__ tabl) {
     const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
-    const double C_HI = 0.01083042469326756;            // ln2/64, low 21 mantissa bits zero
-    const double C_LO = 2.9815858269852933e-12;
-    double t = fma(u, -L, MAGIC);
-    double kf = t - MAGIC;                              // k = rint(-u * 64/ln2)
-    double r = fma(kf, -C_HI, -u);
-    r = fma(kf, -C_LO, r);                              // r = -u - k ln2/64
-    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
+    const double t = fma(u, -c_sig[0], MAGIC);
+    const double kf = t - MAGIC;                        // k = rint(-u * 32/ln2)
+    double r = fma(kf, -c_sig[1], -u);
+    r = fma(kf, -c_sig[2], r);                          // r = -u - k ln2/32
+    double p = fma(r, c_sig[3], c_sig[4]);
+    p = fma(p, r, c_sig[5]);
+    p = fma(p, r, c_sig[6]);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);                                 // exp(r)
-    int k = __double2loint(t);
-    int m = min(max(k >> 6, -1020), 1020);
-    double e = p * tab[k & 63];
+    const int k = __double2loint(t);
+    const int m = min(max(k >> 5, -1020), 1020);
+    double e = p * tabl[(k & 31) << 4];
     e = __hiloint2double(__double2hiint(e) + (m << 20), __double2loint(e));   // * 2^m
-    double den = 1.0 + e;
-    double y = rcp_approx(den);
+    const double den = 1.0 + e;
+    const double y = rcp_approx(den);
     double q = fma(-den, y, 1.0);
     q = fma(q, q, q);
     return fma(y, q, y);
@@ -122,7 +93,7 @@ __device__ __forceinline__ double sigmoid_fast(double u, const double* __restric
 
 // Two independent sigmoids in lock-step (explicit ILP 2: the FP64 pipe issues one warp
 // instruction every 2 cycles and each chain is ~14 dependent FP64 ops deep).
-__device__ __forceinline__ void sigmoid_fast2(double u0, double u1, const double* __restrict__ tab,
+__device__ __forceinline__ void sigmoid_fast2(double u0, double u1, const double* __restrict__ tabl,
                                               double& s0, double& s1) {
     const double MAGIC = 6755399441055744.0;
     const double L = c_sig[0], C_HI = c_sig[1], C_LO = c_sig[2];
@@ -131,14 +102,15 @@ __device__ __forceinline__ void sigmoid_fast2(double u0, double u1, const double
     double r0 = fma(k0, -C_HI, -u0), r1 = fma(k1, -C_HI, -u1);
     r0 = fma(k0, -C_LO, r0); r1 = fma(k1, -C_LO, r1);
     const int i0 = __double2loint(t0), i1 = __double2loint(t1);
-    const double T0 = tab[i0 & 63], T1 = tab[i1 & 63];
-    const double c5 = c_sig[3], c4 = c_sig[4], c3 = c_sig[5];
-    double p0 = fma(r0, c5, c4), p1 = fma(r1, c5, c4);
+    const double T0 = tabl[(i0 & 31) << 4], T1 = tabl[(i1 & 31) << 4];
+    const double c6 = c_sig[3], c5 = c_sig[4], c4 = c_sig[5], c3 = c_sig[6];
+    double p0 = fma(r0, c6, c5), p1 = fma(r1, c6, c5);
+    p0 = fma(p0, r0, c4); p1 = fma(p1, r1, c4);
     p0 = fma(p0, r0, c3); p1 = fma(p1, r1, c3);
     p0 = fma(p0, r0, 0.5); p1 = fma(p1, r1, 0.5);
     p0 = fma(p0, r0, 1.0); p1 = fma(p1, r1, 1.0);
     p0 = fma(p0, r0, 1.0); p1 = fma(p1, r1, 1.0);
-    const int m0 = min(max(i0 >> 6, -1020), 1020), m1 = min(max(i1 >> 6, -1020), 1020);
+    const int m0 = min(max(i0 >> 5, -1020), 1020), m1 = min(max(i1 >> 5, -1020), 1020);
     double e0 = p0 * T0, e1 = p1 * T1;
     e0 = __hiloint2double(__double2hiint(e0) + (m0 << 20), __double2loint(e0));
     e1 = __hiloint2double(__double2hiint(e1) + (m1 << 20), __double2loint(e1));

@@ -46,7 +46,9 @@ struct FlowArgs {
     int W;                  // walkers per CTA
     int P, NP;              // items per walker (pairs + singles), pairs
     int D, DP;              // 2n, padded row length of J
-    int NSV;                // state doubles per walker
+    int NSV;                // doubles of the stage-input state block: NV + D8*DP (E_loc) or NV
+    int NV;                 // vector part: y, L, gDelta, Delta, lapDelta (E_loc: 3D+2) or y(+Delta)
+    int NPAR;               // doubles of each RK partial / derivative block: NV + D*D (E_loc) or NV
     int wstride;            // shared doubles per walker
     int grec;               // doubles per item record (kGRec for MODE_ELOC, 3 otherwise: vx, vy, q)
     int off_G, off_AM, off_u, off_kLx, off_part, off_x0, off_sl;   // offsets inside a walker block
@@ -209,27 +211,59 @@ __device__ __forceinline__ void dmma_chunk(int K, int nch, AF a_of, BF b_of, dou
     for (int c = 0; c < kCH; ++c) { acc[c][0] = e[c][0] + o[c][0]; acc[c][1] = e[c][1] + o[c][1]; }
 }
 
-// Gram matrix M = J J^T (upper block triangle of 8x8 blocks) of every walker.  A task is a
-// run of up to kCH consecutive column blocks of one block row.  J: [D8][DP], rows >= D zero.
-__device__ __forceinline__ void gram_dmma(int W, int D8, int DP, double* wbase, int wstride, int oJ, int off_AM) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    const int g = lane >> 2, t = lane & 3, NB = D8 >> 3;
-    int tpw = 0;                                   // tasks per walker
-    for (int rb = 0; rb < NB; ++rb) tpw += (NB - rb + kCH - 1) / kCH;
-    for (int task = warp; task < W * tpw; task += nwarp) {
-        const int w = task / tpw;
-        int rem = task - w * tpw, rb = 0;
-        for (;; ++rb) { const int c = (NB - rb + kCH - 1) / kCH; if (rem < c) break; rem -= c; }
-        const int cb0 = rb + rem * kCH, nch = min(kCH, NB - cb0);
-        const double* J = wbase + (size_t)w * wstride + oJ;
-        const double* A = J + (8 * rb + g) * DP + t;
-        const double* B = J + (8 * cb0 + g) * DP + t;
-        double acc[kCH][2];
-        dmma_chunk(D8, nch, [&](int k) { return A[k]; }, [&](int c, int k) { return B[c * 8 * DP + k]; }, acc);
-        double* M = wbase + (size_t)w * wstride + off_AM + (8 * rb + g) * DP + 8 * cb0 + 2 * t;
+// Same with an individual A operand per chain: a_of(c, k) -> A_c[g][k + t].
+template <class AF, class BF>
+__device__ __forceinline__ void dmma_chunk_ab(int K, int nch, AF a_of, BF b_of, double (&acc)[kCH][2]) {
+    double e[kCH][2], o[kCH][2];
+#pragma unroll
+    for (int c = 0; c < kCH; ++c) { e[c][0] = e[c][1] = o[c][0] = o[c][1] = 0.0; }
+    int k = 0;
+    for (; k + 8 <= K; k += 8) {
 #pragma unroll
         for (int c = 0; c < kCH; ++c)
-            if (c < nch) *reinterpret_cast<double2*>(M + 8 * c) = make_double2(acc[c][0], acc[c][1]);
+            if (c < nch) {
+                dmma_m8n8k4(e[c][0], e[c][1], a_of(c, k), b_of(c, k));
+                dmma_m8n8k4(o[c][0], o[c][1], a_of(c, k + 4), b_of(c, k + 4));
+            }
+    }
+    if (k < K) {
+#pragma unroll
+        for (int c = 0; c < kCH; ++c)
+            if (c < nch) dmma_m8n8k4(e[c][0], e[c][1], a_of(c, k), b_of(c, k));
+    }
+#pragma unroll
+    for (int c = 0; c < kCH; ++c) { acc[c][0] = e[c][0] + o[c][0]; acc[c][1] = e[c][1] + o[c][1]; }
+}
+
+// Gram matrix M = J J^T (upper block triangle of 8x8 blocks) of every walker.  The
+// W * NB(NB+1)/2 blocks are dealt out evenly: each warp takes a contiguous run of blocks and
+// works on up to kCH of them at once.  J: [D8][DP], rows >= D zero.
+__device__ __forceinline__ void gram_dmma(int W, int D8, int DP, double* wbase, int wstride, int oJ, int off_AM) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3, NB = D8 >> 3, ntri = NB * (NB + 1) / 2;
+    const int total = W * ntri;
+    const int per = (total + nwarp - 1) / nwarp;
+    const int first = warp * per, last = min(total, first + per);
+    for (int b0 = first; b0 < last; b0 += kCH) {
+        const int nch = min(kCH, last - b0);
+        const double* Ap[kCH]; const double* Bp[kCH]; double* Mp[kCH];
+#pragma unroll
+        for (int c = 0; c < kCH; ++c) {
+            const int blk = min(b0 + c, total - 1);
+            const int w = blk / ntri;
+            int rem = blk - w * ntri, rb = 0;
+            while (rem >= NB - rb) { rem -= NB - rb; ++rb; }
+            const int cb = rb + rem;
+            double* base = wbase + (size_t)w * wstride;
+            Ap[c] = base + oJ + (8 * rb + g) * DP + t;
+            Bp[c] = base + oJ + (8 * cb + g) * DP + t;
+            Mp[c] = base + off_AM + (8 * rb + g) * DP + 8 * cb + 2 * t;
+        }
+        double acc[kCH][2];
+        dmma_chunk_ab(D8, nch, [&](int c, int k) { return Ap[c][k]; }, [&](int c, int k) { return Bp[c][k]; }, acc);
+#pragma unroll
+        for (int c = 0; c < kCH; ++c)
+            if (c < nch) *reinterpret_cast<double2*>(Mp[c]) = make_double2(acc[c][0], acc[c][1]);
     }
 }
 
@@ -244,17 +278,18 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
     const int warp = tid >> 5, lane = tid & 31, nwarp = T >> 5;
 
     // ---- shared carve-up -------------------------------------------------------------
-    double* tab = smem;                               // 64
-    double* coef_eta = tab + 64;                      // 6 * even(H_eta)
+    double* tab = smem;                               // kTabDoubles
+    double* coef_eta = tab + kTabDoubles;             // 6 * even(H_eta)
     double* coef_mu = coef_eta + 6 * ((a.H_eta + 1) & ~1);
-    int cbase = 64 + 6 * (((a.H_eta + 1) & ~1) + ((a.H_mu + 1) & ~1));
+    int cbase = kTabDoubles + 6 * (((a.H_eta + 1) & ~1) + ((a.H_mu + 1) & ~1));
     unsigned char* pair_i = reinterpret_cast<unsigned char*>(smem + cbase);   // NP each
     unsigned char* pair_j = pair_i + ((NP + 7) & ~7);
     double* wbase = smem + cbase + 2 * ((NP + 7) / 8);
     if ((wbase - smem) & 1) wbase += 1;
     const int wstride = a.wstride;
 
-    for (int i = tid; i < 64; i += T) tab[i] = c_exp2_64[i];
+    fill_exp_table(tab);
+    const double* tabl = tab + (tid & 15);
     load_mlp_coef(coef_eta, a.eta_w1, a.eta_b1, a.eta_w2, a.H_eta);
     if (has_mu) load_mlp_coef(coef_mu, a.mu_w1, a.mu_b1, a.mu_w2, a.H_mu);
     for (int p = tid; p < NP; p += T) {
@@ -269,7 +304,8 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
     constexpr int oY = 0;
     const int oL = D, oG = 2 * D, oS = 3 * D, oJ = 3 * D + 2;       // ELOC offsets
     const int oDelta = (MODE == MODE_ELOC) ? oS : D;
-    const int oP3 = NSV, oP4 = 2 * NSV, oPO = 3 * NSV, oK = 4 * NSV;
+    const int NV = a.NV, NPAR = a.NPAR;
+    const int oP3 = NSV, oP4 = NSV + NPAR, oPO = NSV + 2 * NPAR, oK = NSV + 3 * NPAR;
 
     // item owned by this thread
     const int it_w = tid / P, it_p = tid - it_w * P;
@@ -322,7 +358,7 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                 double f[4];
                 constexpr int ORD = (MODE == MODE_V) ? 0 : (MODE == MODE_DIV) ? 1 : (MODE == MODE_STASH) ? 2 : 3;
                 // one call for both item kinds: no divergence between pair and single lanes
-                radial_mlp<ORD>(it_pair ? coef_eta : coef_mu, it_pair ? a.H_eta : a.H_mu, d, tab, f);
+                radial_mlp<ORD>(it_pair ? coef_eta : coef_mu, it_pair ? a.H_eta : a.H_mu, d, tabl, f);
                 constexpr int GR = (MODE == MODE_ELOC) ? kGRec : 3;
                 constexpr int GQ = (MODE == MODE_ELOC) ? 6 : 2;
                 double* G = myS + a.off_G + it_p * GR;
@@ -478,10 +514,14 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                             const double* Bp = Jmat + t * DP + 8 * cb0 + g;            // J[k][col]
                             dmma_chunk(D8, nch, [&](int k) { return Ap[k]; },
                                        [&](int c, int k) { return Bp[k * DP + 8 * c]; }, acc);
-                            double* K = Sw + oK + oJ + (8 * rb + g) * DP + 8 * cb0 + 2 * t;
+                            // derivative block keeps J unpadded: [D][D]
+                            double* K = Sw + oK + NV + (8 * rb + g) * D + 8 * cb0 + 2 * t;
+                            if (8 * rb + g < D) {
 #pragma unroll
-                            for (int c = 0; c < kCH; ++c)
-                                if (c < nch) *reinterpret_cast<double2*>(K + 8 * c) = make_double2(acc[c][0], acc[c][1]);
+                                for (int c = 0; c < kCH; ++c)
+                                    if (c < nch && 8 * (cb0 + c) + 2 * t < D)
+                                        *reinterpret_cast<double2*>(K + 8 * c) = make_double2(acc[c][0], acc[c][1]);
+                            }
                         } else {
                             rem -= NB * nchunk;
                             const bool isL = rem < nchunk;                 // L^T A  or  u^T J
@@ -539,53 +579,52 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
             // ======== S4: 3/8-rule RK4 bookkeeping (torchdiffeq rk4_alt_step_func) ========
             for (int w = 0; w < W; ++w) {
                 double* Sw = wbase + (size_t)w * wstride;
-                if ((NSV & 1) == 0) {
-                    // two elements per thread, 128-bit shared-memory accesses
-                    double2* S2 = reinterpret_cast<double2*>(Sw);
-                    double2* P32 = reinterpret_cast<double2*>(Sw + oP3);
-                    double2* P42 = reinterpret_cast<double2*>(Sw + oP4);
-                    double2* PO2 = reinterpret_cast<double2*>(Sw + oPO);
-                    const double2* K2 = reinterpret_cast<const double2*>(Sw + oK);
-                    for (int e = tid; e < NSV / 2; e += T) {
-                        double2 k = K2[e]; k.x *= h; k.y *= h;
-                        if (sub == 0) {
-                            const double2 y0 = S2[e];
-                            P32[e] = make_double2(fma(k.x, -1.0 / 3.0, y0.x), fma(k.y, -1.0 / 3.0, y0.y));
-                            P42[e] = make_double2(y0.x + k.x, y0.y + k.y);
-                            PO2[e] = make_double2(fma(k.x, 0.125, y0.x), fma(k.y, 0.125, y0.y));
-                            S2[e] = make_double2(fma(k.x, 1.0 / 3.0, y0.x), fma(k.y, 1.0 / 3.0, y0.y));
-                        } else if (sub == 1) {
-                            const double2 p3 = P32[e], p4 = P42[e], po = PO2[e];
-                            S2[e] = make_double2(p3.x + k.x, p3.y + k.y);
-                            P42[e] = make_double2(p4.x - k.x, p4.y - k.y);
-                            PO2[e] = make_double2(fma(k.x, 0.375, po.x), fma(k.y, 0.375, po.y));
-                        } else if (sub == 2) {
-                            const double2 p4 = P42[e], po = PO2[e];
-                            S2[e] = make_double2(p4.x + k.x, p4.y + k.y);
-                            PO2[e] = make_double2(fma(k.x, 0.375, po.x), fma(k.y, 0.375, po.y));
-                        } else {
-                            const double2 po = PO2[e];
-                            S2[e] = make_double2(fma(k.x, 0.125, po.x), fma(k.y, 0.125, po.y));
-                        }
+                // element e of the state block <-> element pe of the partial / derivative blocks
+                auto upd = [&](double* s, double* p3, double* p4, double* po, const double* kk) {
+                    const double k = *kk * h;
+                    if (sub == 0) {
+                        const double y0 = *s;
+                        *p3 = fma(k, -1.0 / 3.0, y0); *p4 = y0 + k; *po = fma(k, 0.125, y0);
+                        *s = fma(k, 1.0 / 3.0, y0);
+                    } else if (sub == 1) {
+                        *s = *p3 + k; *p4 -= k; *po = fma(k, 0.375, *po);
+                    } else if (sub == 2) {
+                        *s = *p4 + k; *po = fma(k, 0.375, *po);
+                    } else {
+                        *s = fma(k, 0.125, *po);
                     }
-                } else {
-                    for (int e = tid; e < NSV; e += T) {
-                        const double k = Sw[oK + e] * h;
+                };
+                for (int e = tid; e < NV; e += T) upd(Sw + e, Sw + oP3 + e, Sw + oP4 + e, Sw + oPO + e, Sw + oK + e);
+                if (MODE == MODE_ELOC) {
+                    // J: state rows have stride DP, partial rows stride D; two columns per thread
+                    const int hD = D >> 1;
+                    for (int e = tid; e < D * hD; e += T) {
+                        const int r = e / hD, c = (e - r * hD) * 2;
+                        double2* s2 = reinterpret_cast<double2*>(Sw + NV + r * DP + c);
+                        const int pe = NV + r * D + c;
+                        double2* p3 = reinterpret_cast<double2*>(Sw + oP3 + pe);
+                        double2* p4 = reinterpret_cast<double2*>(Sw + oP4 + pe);
+                        double2* po = reinterpret_cast<double2*>(Sw + oPO + pe);
+                        double2 k = *reinterpret_cast<const double2*>(Sw + oK + pe);
+                        k.x *= h; k.y *= h;
                         if (sub == 0) {
-                            const double y0 = Sw[e];
-                            Sw[oP3 + e] = fma(k, -1.0 / 3.0, y0);
-                            Sw[oP4 + e] = y0 + k;
-                            Sw[oPO + e] = fma(k, 0.125, y0);
-                            Sw[e] = fma(k, 1.0 / 3.0, y0);
+                            const double2 y0 = *s2;
+                            *p3 = make_double2(fma(k.x, -1.0 / 3.0, y0.x), fma(k.y, -1.0 / 3.0, y0.y));
+                            *p4 = make_double2(y0.x + k.x, y0.y + k.y);
+                            *po = make_double2(fma(k.x, 0.125, y0.x), fma(k.y, 0.125, y0.y));
+                            *s2 = make_double2(fma(k.x, 1.0 / 3.0, y0.x), fma(k.y, 1.0 / 3.0, y0.y));
                         } else if (sub == 1) {
-                            Sw[e] = Sw[oP3 + e] + k;
-                            Sw[oP4 + e] -= k;
-                            Sw[oPO + e] = fma(k, 0.375, Sw[oPO + e]);
+                            const double2 a3 = *p3, a4 = *p4, ao = *po;
+                            *s2 = make_double2(a3.x + k.x, a3.y + k.y);
+                            *p4 = make_double2(a4.x - k.x, a4.y - k.y);
+                            *po = make_double2(fma(k.x, 0.375, ao.x), fma(k.y, 0.375, ao.y));
                         } else if (sub == 2) {
-                            Sw[e] = Sw[oP4 + e] + k;
-                            Sw[oPO + e] = fma(k, 0.375, Sw[oPO + e]);
+                            const double2 a4 = *p4, ao = *po;
+                            *s2 = make_double2(a4.x + k.x, a4.y + k.y);
+                            *po = make_double2(fma(k.x, 0.375, ao.x), fma(k.y, 0.375, ao.y));
                         } else {
-                            Sw[e] = fma(k, 0.125, Sw[oPO + e]);
+                            const double2 ao = *po;
+                            *s2 = make_double2(fma(k.x, 0.125, ao.x), fma(k.y, 0.125, ao.y));
                         }
                     }
                 }

@@ -27,11 +27,12 @@ __global__ void __launch_bounds__(512) backflow_kernel(const BackflowArgs a) {
     const int n = a.n, D = 2 * n, P = a.P, NP = a.NP, W = a.W;
     const bool has_mu = a.H_mu > 0;
     double* tab = smem;
-    double* coef_eta = tab + 64;
+    double* coef_eta = tab + kTabDoubles;
     double* coef_mu = coef_eta + 6 * ((a.H_eta + 1) & ~1);
     double* wb = coef_mu + 6 * ((a.H_mu + 1) & ~1);
     const int wstride = D + 3 * P;          // x[D], G[P][3] (vx, vy, q)
-    for (int i = tid; i < 64; i += T) tab[i] = c_exp2_64[i];
+    fill_exp_table(tab);
+    const double* tabl = tab + (tid & 15);
     load_mlp_coef(coef_eta, a.eta_w1, a.eta_b1, a.eta_w2, a.H_eta);
     if (has_mu) load_mlp_coef(coef_mu, a.mu_w1, a.mu_b1, a.mu_w2, a.H_mu);
     const int it_w = tid / P, it_p = tid - it_w * P;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(512) backflow_kernel(const BackflowArgs a) {
             } else { const int i = it_p - NP; rx = x[2 * i]; ry = x[2 * i + 1]; }
             const double d = sqrt(fma(rx, rx, ry * ry));
             double f[4];
-            radial_mlp<1>(pair ? coef_eta : coef_mu, pair ? a.H_eta : a.H_mu, d, tab, f);
+            radial_mlp<1>(pair ? coef_eta : coef_mu, pair ? a.H_eta : a.H_mu, d, tabl, f);
             G[0] = f[0] * rx; G[1] = f[0] * ry;
             G[2] = (pair ? 2.0 : 1.0) * fma(f[1], d, 2.0 * f[0]);
         }
