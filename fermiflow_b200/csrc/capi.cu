@@ -95,7 +95,7 @@ int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t
         const int need = ff::slater_scratch_size(m->n_up, m->n_dn) + 2 * a.D + n * n + a.NP + 8;
         if (need > 4 * a.NPAR) return fail(-2, "internal: finale scratch does not fit");
     }
-    int common = ff::kTabDoubles + 6 * (even(m->H_eta) + even(m->H_mu));
+    int common = ff::kTabDoubles + 6 * (((m->H_eta + 3) & ~3) + ((m->H_mu + 3) & ~3));
     common = even(common) + 2 * ((a.NP + 7) / 8) + 2;
     // E_loc sweep: aim for two resident CTAs per SM (their FP64-bound and shared-memory-bound
     // phases overlap), fall back to one large CTA when a walker does not fit in half an SM.

@@ -121,47 +121,101 @@ __device__ __forceinline__ void sigmoid_fast2(double u0, double u1, const double
     s0 = fma(y0, q0, y0); s1 = fma(y1, q1, y1);
 }
 
+// N sigmoids in lock-step (all loops fully unrolled, arrays live in registers).
+template <int N>
+__device__ __forceinline__ void sigmoid_fastN(const double (&u)[N], const double* __restrict__ tabl, double (&s)[N]) {
+    const double MAGIC = 6755399441055744.0;
+    const double L = c_sig[0], C_HI = c_sig[1], C_LO = c_sig[2];
+    const double c6 = c_sig[3], c5 = c_sig[4], c4 = c_sig[5], c3 = c_sig[6];
+    double t[N], r[N], p[N], T[N], e[N], dn[N], y[N], q[N];
+    int ik[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = fma(u[i], -L, MAGIC);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { ik[i] = __double2loint(t[i]); t[i] -= MAGIC; }
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = fma(t[i], -C_HI, -u[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { r[i] = fma(t[i], -C_LO, r[i]); T[i] = tabl[(ik[i] & 31) << 4]; }
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(r[i], c6, c5);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], c4);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], c3);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], 0.5);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const int m = min(max(ik[i] >> 5, -1020), 1020);
+        e[i] = p[i] * T[i];
+        e[i] = __hiloint2double(__double2hiint(e[i]) + (m << 20), __double2loint(e[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) { dn[i] = 1.0 + e[i]; y[i] = rcp_approx(dn[i]); }
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = fma(-dn[i], y[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = fma(q[i], q[i], q[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) s[i] = fma(y[i], q[i], y[i]);
+}
+
 // Radial MLP f(d) = sum_h w2_h sigmoid(w1_h d + b1_h) and its d-derivatives up to ORD.
 // coef: shared memory, 6 doubles per hidden unit {w1, b1, c0=w2, c1=w2 w1, c2=w2 w1^2,
 // c3=w2 w1^3}; the table is padded to an even number of hidden units with zero rows.
 // Restates MLP.forward / MLP.grad (MLP.py:30-45) for D_in = 1.
+#ifndef FF_MLP_ILP
+#define FF_MLP_ILP 4
+#endif
 template <int ORD>
 __device__ __forceinline__ void radial_mlp(const double* __restrict__ coef, int H, double d,
                                            const double* __restrict__ tab, double (&f)[4]) {
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-    const int H2 = (H + 1) & ~1;
+    constexpr int NI = FF_MLP_ILP;
+    double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    const int HP = ((H + NI - 1) / NI) * NI;        // the table is zero-padded to a multiple of 4
 #pragma unroll 1
-    for (int h = 0; h < H2; h += 2) {
+    for (int h = 0; h < HP; h += NI) {
         const double* c = coef + 6 * h;
-        const double2 wbA = *reinterpret_cast<const double2*>(c);
-        const double2 wbB = *reinterpret_cast<const double2*>(c + 6);
-        double sA, sB;
-        sigmoid_fast2(fma(wbA.x, d, wbA.y), fma(wbB.x, d, wbB.y), tab, sA, sB);
-        const double2 cA01 = *reinterpret_cast<const double2*>(c + 2);
-        const double2 cB01 = *reinterpret_cast<const double2*>(c + 8);
-        a0 = fma(cA01.x, sA, a0); b0 = fma(cB01.x, sB, b0);
-        if (ORD >= 1) {
-            const double sA1 = fma(-sA, sA, sA), sB1 = fma(-sB, sB, sB);       // s (1 - s)
-            a1 = fma(cA01.y, sA1, a1); b1 = fma(cB01.y, sB1, b1);
-            if (ORD >= 2) {
-                const double2 cA23 = *reinterpret_cast<const double2*>(c + 4);
-                const double2 cB23 = *reinterpret_cast<const double2*>(c + 10);
-                const double sA2 = sA1 * fma(-2.0, sA, 1.0), sB2 = sB1 * fma(-2.0, sB, 1.0);
-                a2 = fma(cA23.x, sA2, a2); b2 = fma(cB23.x, sB2, b2);
-                if (ORD >= 3) {
-                    const double sA3 = sA1 * fma(-6.0, sA1, 1.0), sB3 = sB1 * fma(-6.0, sB1, 1.0);
-                    a3 = fma(cA23.y, sA3, a3); b3 = fma(cB23.y, sB3, b3);
+        double u[NI], sg[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const double2 wb = *reinterpret_cast<const double2*>(c + 6 * i);
+            u[i] = fma(wb.x, d, wb.y);
+        }
+        sigmoid_fastN<NI>(u, tab, sg);
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const double2 c01 = *reinterpret_cast<const double2*>(c + 6 * i + 2);
+            const double s0 = sg[i];
+            acc[0][i & 1] = fma(c01.x, s0, acc[0][i & 1]);
+            if (ORD >= 1) {
+                const double s1 = fma(-s0, s0, s0);                      // s (1 - s)
+                acc[1][i & 1] = fma(c01.y, s1, acc[1][i & 1]);
+                if (ORD >= 2) {
+                    const double2 c23 = *reinterpret_cast<const double2*>(c + 6 * i + 4);
+                    const double s2 = s1 * fma(-2.0, s0, 1.0);           // s1 (1 - 2 s)
+                    acc[2][i & 1] = fma(c23.x, s2, acc[2][i & 1]);
+                    if (ORD >= 3) {
+                        const double s3 = s1 * fma(-6.0, s1, 1.0);       // s1 (1 - 6 s1)
+                        acc[3][i & 1] = fma(c23.y, s3, acc[3][i & 1]);
+                    }
                 }
             }
         }
     }
-    f[0] = a0 + b0; f[1] = a1 + b1; f[2] = a2 + b2; f[3] = a3 + b3;
+    f[0] = acc[0][0] + acc[0][1]; f[1] = acc[1][0] + acc[1][1];
+    f[2] = acc[2][0] + acc[2][1]; f[3] = acc[3][0] + acc[3][1];
 }
 
 // Fill the shared coefficient table from the three parameter vectors of one MLP.
 __device__ __forceinline__ void load_mlp_coef(double* coef, const double* w1, const double* b1,
                                               const double* w2, int H) {
-    const int H2 = (H + 1) & ~1;
+    const int H2 = ((H + 3) & ~3);              // zero rows up to a multiple of 4
     for (int h = threadIdx.x; h < H2; h += blockDim.x) {
         double a = 0.0, b = 0.0, c = 0.0;
         if (h < H) { a = w1[h]; b = b1[h]; c = w2[h]; }

@@ -57,13 +57,130 @@ struct FlowArgs {
 // State vector layout (MODE_ELOC): [y:D][L:D][gD:D][Delta, lapDelta][J: D x DP]
 // otherwise:                        [y:D][Delta]
 
+// ---- FP64 tensor-core (DMMA m8n8k4) building blocks --------------------------------------
+// A dependent DMMA chain issues only every ~150 cycles, so every warp task below carries
+// up to 2*CH independent accumulators (CH column blocks x two interleaved halves of K).
+constexpr int kCH = 5;
+
+// C[c] (8x8 each, c < nch) = A(8 x K) * B_c(K x 8).  Lane (g = lane/4, t = lane%4):
+//   a_of(k)    -> A[g][k + t]          (the caller bakes g, t into the functor)
+//   b_of(c, k) -> B_c[k + t][g]
+// K is a multiple of 4.  Results: acc[c][0..1] = C_c[g][2t, 2t+1].
+template <class AF, class BF>
+__device__ __forceinline__ void dmma_chunk(int K, int nch, AF a_of, BF b_of, double (&acc)[kCH][2]) {
+    double e[kCH][2], o[kCH][2];
+#pragma unroll
+    for (int c = 0; c < kCH; ++c) { e[c][0] = e[c][1] = o[c][0] = o[c][1] = 0.0; }
+    int k = 0;
+    for (; k + 8 <= K; k += 8) {
+        const double a0 = a_of(k), a1 = a_of(k + 4);
+#pragma unroll
+        for (int c = 0; c < kCH; ++c)
+            if (c < nch) {
+                dmma_m8n8k4(e[c][0], e[c][1], a0, b_of(c, k));
+                dmma_m8n8k4(o[c][0], o[c][1], a1, b_of(c, k + 4));
+            }
+    }
+    if (k < K) {
+        const double a0 = a_of(k);
+#pragma unroll
+        for (int c = 0; c < kCH; ++c)
+            if (c < nch) dmma_m8n8k4(e[c][0], e[c][1], a0, b_of(c, k));
+    }
+#pragma unroll
+    for (int c = 0; c < kCH; ++c) { acc[c][0] = e[c][0] + o[c][0]; acc[c][1] = e[c][1] + o[c][1]; }
+}
+
+// Same with an individual A operand per chain: a_of(c, k) -> A_c[g][k + t].
+template <class AF, class BF>
+__device__ __forceinline__ void dmma_chunk_ab(int K, int nch, AF a_of, BF b_of, double (&acc)[kCH][2]) {
+    double e[kCH][2], o[kCH][2];
+#pragma unroll
+    for (int c = 0; c < kCH; ++c) { e[c][0] = e[c][1] = o[c][0] = o[c][1] = 0.0; }
+    int k = 0;
+    for (; k + 8 <= K; k += 8) {
+#pragma unroll
+        for (int c = 0; c < kCH; ++c)
+            if (c < nch) {
+                dmma_m8n8k4(e[c][0], e[c][1], a_of(c, k), b_of(c, k));
+                dmma_m8n8k4(o[c][0], o[c][1], a_of(c, k + 4), b_of(c, k + 4));
+            }
+    }
+    if (k < K) {
+#pragma unroll
+        for (int c = 0; c < kCH; ++c)
+            if (c < nch) dmma_m8n8k4(e[c][0], e[c][1], a_of(c, k), b_of(c, k));
+    }
+#pragma unroll
+    for (int c = 0; c < kCH; ++c) { acc[c][0] = e[c][0] + o[c][0]; acc[c][1] = e[c][1] + o[c][1]; }
+}
+
+// Gram matrix M = J J^T (upper block triangle of 8x8 blocks) of every walker.  The
+// W * NB(NB+1)/2 blocks are dealt out evenly: each warp owns a contiguous run of blocks for
+// the whole kernel (GramPlan, computed once) and works on up to kCH of them at once.
+// J: [D8][DP], rows >= D zero.
+struct GramPlan {
+    int nch;                 // blocks of this warp handled by the fast path (<= kCH)
+    int first, last;         // run of blocks of this warp
+    int oA[kCH], oB[kCH], oM[kCH];   // shared-memory offsets (doubles, relative to wbase)
+};
+
+__device__ __forceinline__ void gram_block_offsets(int blk, int W, int D8, int DP, int wstride, int oJ, int off_AM,
+                                                   int g, int t, int& oA, int& oB, int& oM) {
+    const int NB = D8 >> 3, ntri = NB * (NB + 1) / 2;
+    const int w = blk / ntri;
+    int rem = blk - w * ntri, rb = 0;
+    while (rem >= NB - rb) { rem -= NB - rb; ++rb; }
+    const int cb = rb + rem;
+    oA = w * wstride + oJ + (8 * rb + g) * DP + t;
+    oB = w * wstride + oJ + (8 * cb + g) * DP + t;
+    oM = w * wstride + off_AM + (8 * rb + g) * DP + 8 * cb + 2 * t;
+}
+
+__device__ __forceinline__ GramPlan gram_plan(int W, int D8, int DP, int wstride, int oJ, int off_AM) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3, NB = D8 >> 3, total = W * NB * (NB + 1) / 2;
+    const int per = (total + nwarp - 1) / nwarp;
+    GramPlan p;
+    p.first = min(total, warp * per);
+    p.last = min(total, p.first + per);
+    p.nch = min(kCH, p.last - p.first);
+#pragma unroll
+    for (int c = 0; c < kCH; ++c)
+        gram_block_offsets(min(p.first + c, total - 1), W, D8, DP, wstride, oJ, off_AM, g, t, p.oA[c], p.oB[c], p.oM[c]);
+    return p;
+}
+
+__device__ __forceinline__ void gram_run(const GramPlan& p, int W, int D8, int DP, double* wbase, int wstride,
+                                         int oJ, int off_AM) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double acc[kCH][2];
+    if (p.nch > 0) {
+        dmma_chunk_ab(D8, p.nch, [&](int c, int k) { return wbase[p.oA[c] + k]; },
+                      [&](int c, int k) { return wbase[p.oB[c] + k]; }, acc);
+#pragma unroll
+        for (int c = 0; c < kCH; ++c)
+            if (c < p.nch) *reinterpret_cast<double2*>(wbase + p.oM[c]) = make_double2(acc[c][0], acc[c][1]);
+    }
+    for (int b0 = p.first + kCH; b0 < p.last; b0 += kCH) {       // more than kCH blocks per warp: generic path
+        const int nch = min(kCH, p.last - b0);
+        int oA[kCH], oB[kCH], oM[kCH];
+#pragma unroll
+        for (int c = 0; c < kCH; ++c)
+            gram_block_offsets(min(b0 + c, p.last - 1), W, D8, DP, wstride, oJ, off_AM, g, t, oA[c], oB[c], oM[c]);
+        dmma_chunk_ab(D8, nch, [&](int c, int k) { return wbase[oA[c] + k]; },
+                      [&](int c, int k) { return wbase[oB[c] + k]; }, acc);
+#pragma unroll
+        for (int c = 0; c < kCH; ++c)
+            if (c < nch) *reinterpret_cast<double2*>(wbase + oM[c]) = make_double2(acc[c][0], acc[c][1]);
+    }
+}
+
 // Base-distribution end of the E_loc sweep (MODE_ELOC): at z = flow^-1(x) evaluate
 // log p0 = 2 (log|det_up| + log|det_dn|) (base_dist.py:48-56) with gradient g0 and the
 // Hessian contraction <H0, J J^T>, then assemble
 //   log p = log p0 - Delta,  grad = J^T g0 - gDelta,  lap = <H0, JJ^T> + g0.L - lapDelta,
 //   E_loc = -1/4 lap - 1/8 |grad|^2 + V(x)                       (VMC.py:48-55).
-__device__ __forceinline__ void gram_dmma(int W, int D8, int DP, double* wbase, int wstride, int oJ, int off_AM);
-
 __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
                             const unsigned char* pair_i, const unsigned char* pair_j) {
     const int tid = threadIdx.x, T = blockDim.x;
@@ -82,7 +199,10 @@ __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
                      return a.orb + (size_t)row * n; });
 
     // M = J J^T at the end point (upper block triangle), into the AM buffer
-    gram_dmma(W, (D + 7) & ~7, DP, wbase, a.wstride, oJ, a.off_AM);
+    {
+        const GramPlan gp = gram_plan(W, (D + 7) & ~7, DP, a.wstride, oJ, a.off_AM);
+        gram_run(gp, W, (D + 7) & ~7, DP, wbase, a.wstride, oJ, a.off_AM);
+    }
     // g0 and the per-(i,j) Hessian contraction terms
     for (int s = 0; s < 2; ++s) {
         const SlBlk blk = slater_blk(s, n, a.n_up);
@@ -177,96 +297,6 @@ __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
     __syncthreads();
 }
 
-// ---- FP64 tensor-core (DMMA m8n8k4) building blocks --------------------------------------
-// A dependent DMMA chain issues only every ~150 cycles, so every warp task below carries
-// up to 2*CH independent accumulators (CH column blocks x two interleaved halves of K).
-constexpr int kCH = 5;
-
-// C[c] (8x8 each, c < nch) = A(8 x K) * B_c(K x 8).  Lane (g = lane/4, t = lane%4):
-//   a_of(k)    -> A[g][k + t]          (the caller bakes g, t into the functor)
-//   b_of(c, k) -> B_c[k + t][g]
-// K is a multiple of 4.  Results: acc[c][0..1] = C_c[g][2t, 2t+1].
-template <class AF, class BF>
-__device__ __forceinline__ void dmma_chunk(int K, int nch, AF a_of, BF b_of, double (&acc)[kCH][2]) {
-    double e[kCH][2], o[kCH][2];
-#pragma unroll
-    for (int c = 0; c < kCH; ++c) { e[c][0] = e[c][1] = o[c][0] = o[c][1] = 0.0; }
-    int k = 0;
-    for (; k + 8 <= K; k += 8) {
-        const double a0 = a_of(k), a1 = a_of(k + 4);
-#pragma unroll
-        for (int c = 0; c < kCH; ++c)
-            if (c < nch) {
-                dmma_m8n8k4(e[c][0], e[c][1], a0, b_of(c, k));
-                dmma_m8n8k4(o[c][0], o[c][1], a1, b_of(c, k + 4));
-            }
-    }
-    if (k < K) {
-        const double a0 = a_of(k);
-#pragma unroll
-        for (int c = 0; c < kCH; ++c)
-            if (c < nch) dmma_m8n8k4(e[c][0], e[c][1], a0, b_of(c, k));
-    }
-#pragma unroll
-    for (int c = 0; c < kCH; ++c) { acc[c][0] = e[c][0] + o[c][0]; acc[c][1] = e[c][1] + o[c][1]; }
-}
-
-// Same with an individual A operand per chain: a_of(c, k) -> A_c[g][k + t].
-template <class AF, class BF>
-__device__ __forceinline__ void dmma_chunk_ab(int K, int nch, AF a_of, BF b_of, double (&acc)[kCH][2]) {
-    double e[kCH][2], o[kCH][2];
-#pragma unroll
-    for (int c = 0; c < kCH; ++c) { e[c][0] = e[c][1] = o[c][0] = o[c][1] = 0.0; }
-    int k = 0;
-    for (; k + 8 <= K; k += 8) {
-#pragma unroll
-        for (int c = 0; c < kCH; ++c)
-            if (c < nch) {
-                dmma_m8n8k4(e[c][0], e[c][1], a_of(c, k), b_of(c, k));
-                dmma_m8n8k4(o[c][0], o[c][1], a_of(c, k + 4), b_of(c, k + 4));
-            }
-    }
-    if (k < K) {
-#pragma unroll
-        for (int c = 0; c < kCH; ++c)
-            if (c < nch) dmma_m8n8k4(e[c][0], e[c][1], a_of(c, k), b_of(c, k));
-    }
-#pragma unroll
-    for (int c = 0; c < kCH; ++c) { acc[c][0] = e[c][0] + o[c][0]; acc[c][1] = e[c][1] + o[c][1]; }
-}
-
-// Gram matrix M = J J^T (upper block triangle of 8x8 blocks) of every walker.  The
-// W * NB(NB+1)/2 blocks are dealt out evenly: each warp takes a contiguous run of blocks and
-// works on up to kCH of them at once.  J: [D8][DP], rows >= D zero.
-__device__ __forceinline__ void gram_dmma(int W, int D8, int DP, double* wbase, int wstride, int oJ, int off_AM) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    const int g = lane >> 2, t = lane & 3, NB = D8 >> 3, ntri = NB * (NB + 1) / 2;
-    const int total = W * ntri;
-    const int per = (total + nwarp - 1) / nwarp;
-    const int first = warp * per, last = min(total, first + per);
-    for (int b0 = first; b0 < last; b0 += kCH) {
-        const int nch = min(kCH, last - b0);
-        const double* Ap[kCH]; const double* Bp[kCH]; double* Mp[kCH];
-#pragma unroll
-        for (int c = 0; c < kCH; ++c) {
-            const int blk = min(b0 + c, total - 1);
-            const int w = blk / ntri;
-            int rem = blk - w * ntri, rb = 0;
-            while (rem >= NB - rb) { rem -= NB - rb; ++rb; }
-            const int cb = rb + rem;
-            double* base = wbase + (size_t)w * wstride;
-            Ap[c] = base + oJ + (8 * rb + g) * DP + t;
-            Bp[c] = base + oJ + (8 * cb + g) * DP + t;
-            Mp[c] = base + off_AM + (8 * rb + g) * DP + 8 * cb + 2 * t;
-        }
-        double acc[kCH][2];
-        dmma_chunk_ab(D8, nch, [&](int c, int k) { return Ap[c][k]; }, [&](int c, int k) { return Bp[c][k]; }, acc);
-#pragma unroll
-        for (int c = 0; c < kCH; ++c)
-            if (c < nch) *reinterpret_cast<double2*>(Mp[c]) = make_double2(acc[c][0], acc[c][1]);
-    }
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
     extern __shared__ __align__(16) double smem[];
@@ -280,8 +310,8 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
     // ---- shared carve-up -------------------------------------------------------------
     double* tab = smem;                               // kTabDoubles
     double* coef_eta = tab + kTabDoubles;             // 6 * even(H_eta)
-    double* coef_mu = coef_eta + 6 * ((a.H_eta + 1) & ~1);
-    int cbase = kTabDoubles + 6 * (((a.H_eta + 1) & ~1) + ((a.H_mu + 1) & ~1));
+    double* coef_mu = coef_eta + 6 * ((a.H_eta + 3) & ~3);
+    int cbase = kTabDoubles + 6 * (((a.H_eta + 3) & ~3) + ((a.H_mu + 3) & ~3));
     unsigned char* pair_i = reinterpret_cast<unsigned char*>(smem + cbase);   // NP each
     unsigned char* pair_j = pair_i + ((NP + 7) & ~7);
     double* wbase = smem + cbase + 2 * ((NP + 7) / 8);
@@ -306,6 +336,9 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
     const int oDelta = (MODE == MODE_ELOC) ? oS : D;
     const int NV = a.NV, NPAR = a.NPAR;
     const int oP3 = NSV, oP4 = NSV + NPAR, oPO = NSV + 2 * NPAR, oK = NSV + 3 * NPAR;
+
+    GramPlan gplan;
+    if (MODE == MODE_ELOC) gplan = gram_plan(W, D8, DP, wstride, oJ, a.off_AM);
 
     // item owned by this thread
     const int it_w = tid / P, it_p = tid - it_w * P;
@@ -402,7 +435,7 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
             }
             FF_TICK(1);
             if (MODE == MODE_ELOC) {
-                gram_dmma(W, D8, DP, wbase, wstride, oJ, a.off_AM);
+                gram_run(gplan, W, D8, DP, wbase, wstride, oJ, a.off_AM);
                 FF_TICK(2);
                 __syncthreads();
                 FF_TICK(3);
@@ -493,57 +526,57 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
             FF_TICK(7);
             // ======== S3: derivative of the whole state ===================================
             if (MODE == MODE_ELOC) {
-                // K.J = A J, K.L = A L + kLx, K.gD = -(u^T J) on the FP64 tensor cores.  Tasks
-                // per walker: NB block rows of K.J (chunks of kCH column blocks) and two
-                // "row vector x matrix" products (L^T A, A symmetric; u^T J).
+                // K.J = A J on the FP64 tensor cores: one warp task per block row (chunks of kCH
+                // column blocks).  The two small products K.L = A L + kLx and K.gD = -(u^T J) run
+                // as plain DFMA dot products on the last two warps, which have no row task at N=20.
                 {
                     const int g = lane >> 2, t = lane & 3, NB = D8 >> 3;
                     const int nchunk = (NB + kCH - 1) / kCH;
-                    const int tpw = NB * nchunk + 2 * nchunk;
+                    const int tpw = NB * nchunk;
                     for (int task = warp; task < W * tpw; task += nwarp) {
                         const int w = task / tpw;
-                        int rem = task - w * tpw;
+                        const int rem = task - w * tpw;
                         double* Sw = wbase + (size_t)w * wstride;
-                        const double* Amat = Sw + a.off_AM;
-                        const double* Jmat = Sw + oJ;
                         double acc[kCH][2];
-                        if (rem < NB * nchunk) {
-                            const int rb = rem / nchunk, ch = rem - rb * nchunk;
-                            const int cb0 = ch * kCH, nch = min(kCH, NB - cb0);
-                            const double* Ap = Amat + (8 * rb + g) * DP + t;           // A[row][k]
-                            const double* Bp = Jmat + t * DP + 8 * cb0 + g;            // J[k][col]
-                            dmma_chunk(D8, nch, [&](int k) { return Ap[k]; },
-                                       [&](int c, int k) { return Bp[k * DP + 8 * c]; }, acc);
-                            // derivative block keeps J unpadded: [D][D]
-                            double* K = Sw + oK + NV + (8 * rb + g) * D + 8 * cb0 + 2 * t;
-                            if (8 * rb + g < D) {
+                        const int rb = rem / nchunk, ch = rem - rb * nchunk;
+                        const int cb0 = ch * kCH, nch = min(kCH, NB - cb0);
+                        const double* Ap = Sw + a.off_AM + (8 * rb + g) * DP + t;      // A[row][k]
+                        const double* Bp = Sw + oJ + t * DP + 8 * cb0 + g;             // J[k][col]
+                        dmma_chunk(D8, nch, [&](int k) { return Ap[k]; },
+                                   [&](int c, int k) { return Bp[k * DP + 8 * c]; }, acc);
+                        // derivative block keeps J unpadded: [D][D]
+                        double* K = Sw + oK + NV + (8 * rb + g) * D + 8 * cb0 + 2 * t;
+                        if (8 * rb + g < D) {
 #pragma unroll
-                                for (int c = 0; c < kCH; ++c)
-                                    if (c < nch && 8 * (cb0 + c) + 2 * t < D)
-                                        *reinterpret_cast<double2*>(K + 8 * c) = make_double2(acc[c][0], acc[c][1]);
-                            }
-                        } else {
-                            rem -= NB * nchunk;
-                            const bool isL = rem < nchunk;                 // L^T A  or  u^T J
-                            const int ch = isL ? rem : rem - nchunk;
-                            const int cb0 = ch * kCH, nch = min(kCH, NB - cb0);
-                            const double* vec = isL ? Sw + oL : Sw + a.off_u;
-                            const double* Bp = (isL ? Amat : Jmat) + t * DP + 8 * cb0 + g;
-                            dmma_chunk(D8, nch, [&](int k) { return (g == 0 && k + t < D) ? vec[k + t] : 0.0; },
-                                       [&](int c, int k) { return Bp[k * DP + 8 * c]; }, acc);
-                            if (g == 0) {
-#pragma unroll
-                                for (int c = 0; c < kCH; ++c)
-                                    if (c < nch) {
-#pragma unroll
-                                        for (int q = 0; q < 2; ++q) {
-                                            const int col = 8 * (cb0 + c) + 2 * t + q;
-                                            if (col < D) {
-                                                if (isL) (Sw + oK)[oL + col] = acc[c][q] + (Sw + a.off_kLx)[col];
-                                                else (Sw + oK)[oG + col] = -acc[c][q];
-                                            }
-                                        }
-                                    }
+                            for (int c = 0; c < kCH; ++c)
+                                if (c < nch && 8 * (cb0 + c) + 2 * t < D)
+                                    *reinterpret_cast<double2*>(K + 8 * c) = make_double2(acc[c][0], acc[c][1]);
+                        }
+                    }
+                    const int vt = T - 1 - tid;                 // 0 .. 63 on the last two warps
+                    if (vt < 64) {
+                        for (int q = vt; q < W * 2 * D; q += 64) {
+                            const int w = q / (2 * D), e = q - w * 2 * D;
+                            double* Sw = wbase + (size_t)w * wstride;
+                            double acc0 = 0.0, acc1 = 0.0;
+                            if (e < D) {
+                                const double* A = Sw + a.off_AM + e * DP;
+                                const double* L = Sw + oL;
+                                for (int k = 0; k < D; k += 2) {
+                                    const double2 av = *reinterpret_cast<const double2*>(A + k);
+                                    const double2 lv = *reinterpret_cast<const double2*>(L + k);
+                                    acc0 = fma(av.x, lv.x, acc0); acc1 = fma(av.y, lv.y, acc1);
+                                }
+                                (Sw + oK)[oL + e] = acc0 + acc1 + (Sw + a.off_kLx)[e];
+                            } else {
+                                const int c = e - D;
+                                const double* u = Sw + a.off_u;
+                                const double* J = Sw + oJ + c;
+                                for (int k = 0; k < D; k += 2) {
+                                    acc0 = fma(u[k], J[k * DP], acc0);
+                                    acc1 = fma(u[k + 1], J[(k + 1) * DP], acc1);
+                                }
+                                (Sw + oK)[oG + c] = -(acc0 + acc1);
                             }
                         }
                     }
@@ -596,10 +629,12 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                 };
                 for (int e = tid; e < NV; e += T) upd(Sw + e, Sw + oP3 + e, Sw + oP4 + e, Sw + oPO + e, Sw + oK + e);
                 if (MODE == MODE_ELOC) {
-                    // J: state rows have stride DP, partial rows stride D; two columns per thread
+                    // J: state rows have stride DP, partial rows stride D; one row per warp trip,
+                    // two columns per lane (no integer division in the loop)
                     const int hD = D >> 1;
-                    for (int e = tid; e < D * hD; e += T) {
-                        const int r = e / hD, c = (e - r * hD) * 2;
+                    for (int r = warp; r < D; r += nwarp)
+                    for (int c2 = lane; c2 < hD; c2 += 32) {
+                        const int c = 2 * c2;
                         double2* s2 = reinterpret_cast<double2*>(Sw + NV + r * DP + c);
                         const int pe = NV + r * D + c;
                         double2* p3 = reinterpret_cast<double2*>(Sw + oP3 + pe);

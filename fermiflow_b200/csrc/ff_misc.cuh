@@ -28,8 +28,8 @@ __global__ void __launch_bounds__(512) backflow_kernel(const BackflowArgs a) {
     const bool has_mu = a.H_mu > 0;
     double* tab = smem;
     double* coef_eta = tab + kTabDoubles;
-    double* coef_mu = coef_eta + 6 * ((a.H_eta + 1) & ~1);
-    double* wb = coef_mu + 6 * ((a.H_mu + 1) & ~1);
+    double* coef_mu = coef_eta + 6 * ((a.H_eta + 3) & ~3);
+    double* wb = coef_mu + 6 * ((a.H_mu + 3) & ~3);
     const int wstride = D + 3 * P;          // x[D], G[P][3] (vx, vy, q)
     fill_exp_table(tab);
     const double* tabl = tab + (tid & 15);
