@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 #include "../../include/fermiflow_b200.h"
@@ -70,27 +71,12 @@ int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t
     a.eta_w1 = m->eta_w1; a.eta_b1 = m->eta_b1; a.eta_w2 = m->eta_w2;
     a.mu_w1 = m->mu_w1; a.mu_b1 = m->mu_b1; a.mu_w2 = m->mu_w2;
     a.nsteps = m->nsteps;
-    a.D = 2 * n;
-    a.NP = n * (n - 1) / 2;
-    a.P = a.NP + (m->H_mu > 0 ? n : 0);
-    if (a.P < 1) return fail(-1, "a single particle without one-body backflow has no velocity field");
     const bool eloc = mode == ff::MODE_ELOC;
-    const int D8 = (a.D + 7) & ~7;
-    a.DP = eloc ? D8 + 4 : a.D;              // DP mod 16 in {4, 12}: conflict-free DMMA fragments
-    a.NV = eloc ? 3 * a.D + 2 : a.D + (mode >= ff::MODE_DIV ? 1 : 0);
-    a.NSV = eloc ? a.NV + D8 * a.DP : a.NV;
-    a.NPAR = eloc ? a.NV + a.D * a.D : a.NV;
-    if (eloc) { a.NSV = even(a.NSV); a.NPAR = even(a.NPAR); }
-    int off = even(a.NSV + 4 * a.NPAR);
-    a.grec = eloc ? ff::kGRec : 3;
-    a.off_G = off; off = even(off + a.P * a.grec);
-    a.off_AM = off; if (eloc) off = even(off + D8 * a.DP);
-    a.off_u = off; if (eloc) off += a.D;
-    a.off_kLx = off; if (eloc) off += a.D;
-    a.off_part = off; off = even(off + 2 * n);
-    a.off_x0 = off; if (eloc) off += a.D;
-    a.off_sl = a.NSV;
-    a.wstride = even(off);
+    const ff::FlowGeom g = ff::flow_geom(mode, n, m->H_mu > 0);
+    a.D = g.D; a.NP = g.NP; a.P = g.P; a.DP = g.DP; a.NV = g.NV; a.NSV = g.NSV; a.NPAR = g.NPAR; a.grec = g.grec;
+    a.off_G = g.off_G; a.off_AM = g.off_AM; a.off_u = g.off_u; a.off_kLx = g.off_kLx; a.off_part = g.off_part;
+    a.off_x0 = g.off_x0; a.off_sl = g.off_sl; a.wstride = g.wstride;
+    if (a.P < 1) return fail(-1, "a single particle without one-body backflow has no velocity field");
     if (eloc) {
         const int need = ff::slater_scratch_size(m->n_up, m->n_dn) + 2 * a.D + n * n + a.NP + 8;
         if (need > 4 * a.NPAR) return fail(-2, "internal: finale scratch does not fit");
@@ -121,21 +107,30 @@ int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t
     return 0;
 }
 
-template <int MODE>
-int launch_flow(ff::FlowArgs& a, int threads, size_t smem, cudaStream_t st) {
+template <class K>
+int launch_flow_kernel(K kernel, ff::FlowArgs& a, int threads, size_t smem, cudaStream_t st) {
     const DevInfo di = dev_info();
-    FF_CUDA(cudaFuncSetAttribute(ff::flow_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FF_CUDA(cudaFuncSetAttribute(ff::flow_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     int occ = 0;
-    FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ff::flow_kernel<MODE>, threads, smem));
+    FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
     if (occ < 1) return fail(-2, "flow kernel does not fit on an SM (threads %d, smem %zu)", threads, smem);
     long long nb = (a.B + a.W - 1) / a.W;
     long long grid = (long long)di.sms * occ;
     if (grid > nb) grid = nb;
     if (grid < 1) return 0;
-    ff::flow_kernel<MODE><<<(unsigned)grid, threads, smem, st>>>(a);
+    kernel<<<(unsigned)grid, threads, smem, st>>>(a);
     FF_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int MODE>
+int launch_flow(ff::FlowArgs& a, int threads, size_t smem, cudaStream_t st) {
+    if (MODE == ff::MODE_ELOC && a.W == 1 && a.H_mu > 0 && getenv("FF_NO_STATIC") == nullptr) {
+        // statically specialised sweeps for the benchmark sizes (BASELINE.json configs)
+        if (a.n == 20) return launch_flow_kernel(ff::flow_kernel_eloc_static<20, 1>, a, threads, smem, st);
+    }
+    return launch_flow_kernel(ff::flow_kernel<MODE>, a, threads, smem, st);
 }
 
 }  // namespace

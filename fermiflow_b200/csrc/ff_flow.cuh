@@ -57,6 +57,35 @@ struct FlowArgs {
 // State vector layout (MODE_ELOC): [y:D][L:D][gD:D][Delta, lapDelta][J: D x DP]
 // otherwise:                        [y:D][Delta]
 
+// Launch geometry shared by host planning (capi.cu) and the statically specialised kernels.
+struct FlowGeom {
+    int n, D, D8, DP, NP, P, NV, NSV, NPAR, grec;
+    int off_G, off_AM, off_u, off_kLx, off_part, off_x0, off_sl, wstride, threads1;
+};
+__host__ __device__ constexpr int ff_even(int x) { return (x + 1) & ~1; }
+__host__ __device__ constexpr FlowGeom flow_geom(int mode, int n, bool has_mu) {
+    FlowGeom g{};
+    const bool eloc = mode == MODE_ELOC;
+    g.n = n; g.D = 2 * n; g.D8 = (g.D + 7) & ~7;
+    g.NP = n * (n - 1) / 2; g.P = g.NP + (has_mu ? n : 0);
+    g.DP = eloc ? g.D8 + 4 : g.D;                 // DP mod 16 in {4, 12}: conflict-free DMMA fragments
+    g.NV = eloc ? 3 * g.D + 2 : g.D + (mode >= MODE_DIV ? 1 : 0);
+    g.NSV = eloc ? ff_even(g.NV + g.D8 * g.DP) : g.NV;
+    g.NPAR = eloc ? ff_even(g.NV + g.D * g.D) : g.NV;
+    g.grec = eloc ? kGRec : 3;
+    int off = ff_even(g.NSV + 4 * g.NPAR);
+    g.off_G = off; off = ff_even(off + g.P * g.grec);
+    g.off_AM = off; if (eloc) off = ff_even(off + g.D8 * g.DP);
+    g.off_u = off; if (eloc) off += g.D;
+    g.off_kLx = off; if (eloc) off += g.D;
+    g.off_part = off; off = ff_even(off + 2 * n);
+    g.off_x0 = off; if (eloc) off += g.D;
+    g.off_sl = g.NSV;
+    g.wstride = ff_even(off);
+    g.threads1 = ((g.P + 31) / 32) * 32 < 64 ? 64 : ((g.P + 31) / 32) * 32;
+    return g;
+}
+
 // ---- FP64 tensor-core (DMMA m8n8k4) building blocks --------------------------------------
 // A dependent DMMA chain issues only every ~150 cycles, so every warp task below carries
 // up to 2*CH independent accumulators (CH column blocks x two interleaved halves of K).
@@ -297,14 +326,23 @@ __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
     __syncthreads();
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
+// SN > 0 fixes the particle number (and SMU the presence of the one-body MLP) at compile time:
+// every loop bound, offset and index division below then folds to a constant and the short
+// latency-bound phases unroll.  SN = 0 is the generic run-time version.
+template <int MODE, int SN, int SMU>
+__device__ __forceinline__ void flow_body(const FlowArgs& a) {
     extern __shared__ __align__(16) double smem[];
-    const int tid = threadIdx.x, T = blockDim.x;
-    const int n = a.n, D = a.D, DP = a.DP, P = a.P, NP = a.NP, W = a.W, NSV = a.NSV;
+    constexpr bool kS = SN > 0;
+    constexpr FlowGeom GS = flow_geom(MODE, kS ? SN : 2, SMU != 0);
+    const int tid = threadIdx.x, T = kS ? GS.threads1 : (int)blockDim.x;
+    const int n = kS ? GS.n : a.n, D = kS ? GS.D : a.D, DP = kS ? GS.DP : a.DP, P = kS ? GS.P : a.P;
+    const int NP = kS ? GS.NP : a.NP, W = kS ? 1 : a.W, NSV = kS ? GS.NSV : a.NSV;
+    const int off_G = kS ? GS.off_G : a.off_G, off_AM = kS ? GS.off_AM : a.off_AM, off_u = kS ? GS.off_u : a.off_u;
+    const int off_kLx = kS ? GS.off_kLx : a.off_kLx, off_part = kS ? GS.off_part : a.off_part;
+    const int off_x0 = kS ? GS.off_x0 : a.off_x0;
     const int D8 = (D + 7) & ~7;
-    (void)DP; (void)D8;
-    const bool has_mu = a.H_mu > 0;
+    (void)DP; (void)D8; (void)off_AM; (void)off_u; (void)off_kLx; (void)off_x0;
+    const bool has_mu = kS ? (SMU != 0) : (a.H_mu > 0);
     const int warp = tid >> 5, lane = tid & 31, nwarp = T >> 5;
 
     // ---- shared carve-up -------------------------------------------------------------
@@ -316,7 +354,7 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
     unsigned char* pair_j = pair_i + ((NP + 7) & ~7);
     double* wbase = smem + cbase + 2 * ((NP + 7) / 8);
     if ((wbase - smem) & 1) wbase += 1;
-    const int wstride = a.wstride;
+    const int wstride = kS ? GS.wstride : a.wstride;
 
     fill_exp_table(tab);
     const double* tabl = tab + (tid & 15);
@@ -334,11 +372,11 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
     constexpr int oY = 0;
     const int oL = D, oG = 2 * D, oS = 3 * D, oJ = 3 * D + 2;       // ELOC offsets
     const int oDelta = (MODE == MODE_ELOC) ? oS : D;
-    const int NV = a.NV, NPAR = a.NPAR;
+    const int NV = kS ? GS.NV : a.NV, NPAR = kS ? GS.NPAR : a.NPAR;
     const int oP3 = NSV, oP4 = NSV + NPAR, oPO = NSV + 2 * NPAR, oK = NSV + 3 * NPAR;
 
     GramPlan gplan;
-    if (MODE == MODE_ELOC) gplan = gram_plan(W, D8, DP, wstride, oJ, a.off_AM);
+    if (MODE == MODE_ELOC) gplan = gram_plan(W, D8, DP, wstride, oJ, off_AM);
 
     // item owned by this thread
     const int it_w = tid / P, it_p = tid - it_w * P;
@@ -362,7 +400,7 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                 if (e < D) {
                     // padding walkers get a harmless, well separated configuration
                     v = (b < a.B) ? a.x_in[b * D + e] : (double)(e >> 1) + 0.37 * (e & 1);
-                    if (MODE == MODE_ELOC) (Sw + a.off_x0)[e] = v;
+                    if (MODE == MODE_ELOC) (Sw + off_x0)[e] = v;
                 } else if (MODE == MODE_ELOC && e >= oJ) {
                     const int r = (e - oJ) / DP, c = (e - oJ) - r * DP;
                     v = (r == c && r < D) ? 1.0 : 0.0;
@@ -370,7 +408,7 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                 Sw[e] = v;
             }
             if (MODE == MODE_ELOC)
-                for (int e = tid; e < D8 * DP; e += T) (Sw + a.off_AM)[e] = 0.0;
+                for (int e = tid; e < D8 * DP; e += T) (Sw + off_AM)[e] = 0.0;
         }
         __syncthreads();
 
@@ -394,7 +432,7 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                 radial_mlp<ORD>(it_pair ? coef_eta : coef_mu, it_pair ? a.H_eta : a.H_mu, d, tabl, f);
                 constexpr int GR = (MODE == MODE_ELOC) ? kGRec : 3;
                 constexpr int GQ = (MODE == MODE_ELOC) ? 6 : 2;
-                double* G = myS + a.off_G + it_p * GR;
+                double* G = myS + off_G + it_p * GR;
                 cf = f[0];
                 G[0] = cf * rx;
                 G[1] = cf * ry;
@@ -435,13 +473,13 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
             }
             FF_TICK(1);
             if (MODE == MODE_ELOC) {
-                gram_run(gplan, W, D8, DP, wbase, wstride, oJ, a.off_AM);
+                gram_run(gplan, W, D8, DP, wbase, wstride, oJ, off_AM);
                 FF_TICK(2);
                 __syncthreads();
                 FF_TICK(3);
                 // ======== S1: second-derivative contractions per item ====================
                 if (it_valid) {
-                    const double* M = myS + a.off_AM;
+                    const double* M = myS + off_AM;
                     const int i2 = 2 * it_i, j2 = 2 * it_j;
                     double w00, w01, w11;
                     if (it_pair) {
@@ -453,7 +491,7 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                     }
                     const double wrx = fma(w00, rx, w01 * ry), wry = fma(w01, rx, w11 * ry);
                     const double trw = w00 + w11, rwr = fma(rx, wrx, ry * wry);
-                    double* G = myS + a.off_G + it_p * kGRec;
+                    double* G = myS + off_G + it_p * kGRec;
                     G[4] = fma(ca, fma(2.0, wrx, trw * rx), cb * rwr * rx);
                     G[5] = fma(ca, fma(2.0, wry, trw * ry), cb * rwr * ry);
                     G[7] = fma(ccq, trw, ceq * rwr);
@@ -468,7 +506,7 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                 constexpr int NC = (MODE == MODE_ELOC) ? kGRec : (MODE >= MODE_DIV ? 3 : 2);
                 for (int w = 0; w < W; ++w) {
                     double* Sw = wbase + (size_t)w * wstride;
-                    const double* G = Sw + a.off_G;
+                    const double* G = Sw + off_G;
                     for (int g = tid; g < n * NC; g += T) {
                         const int i = g / NC, cc = g - i * NC;
                         const int c = (MODE == MODE_ELOC) ? cc : (cc == 2 ? 6 : cc);   // logical quantity
@@ -500,11 +538,11 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                         if (c == 6 || c == 7) acc *= 0.5;
                         if (has_mu) acc += G[(NP + i) * GRg + gc];
                         if (c < 2) (Sw + oK)[oY + 2 * i + c] = acc;
-                        else if (c < 4) (Sw + a.off_u)[2 * i + c - 2] = acc;
-                        else if (c < 6) (Sw + a.off_kLx)[2 * i + c - 4] = acc;
-                        else if (c < 8) (Sw + a.off_part)[(c - 6) * n + i] = acc;
+                        else if (c < 4) (Sw + off_u)[2 * i + c - 2] = acc;
+                        else if (c < 6) (Sw + off_kLx)[2 * i + c - 4] = acc;
+                        else if (c < 8) (Sw + off_part)[(c - 6) * n + i] = acc;
                         else {
-                            double* A = Sw + a.off_AM;
+                            double* A = Sw + off_AM;
                             if (c == 8) A[(2 * i) * DP + 2 * i] = acc;
                             else if (c == 9) { A[(2 * i) * DP + 2 * i + 1] = acc; A[(2 * i + 1) * DP + 2 * i] = acc; }
                             else A[(2 * i + 1) * DP + 2 * i + 1] = acc;
@@ -512,7 +550,7 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                     }
                 }
                 if (MODE == MODE_ELOC && it_valid && it_pair) {
-                    double* A = myS + a.off_AM;
+                    double* A = myS + off_AM;
                     const double a00 = -fma(ca * rx, rx, cf), a01 = -(ca * rx * ry), a11 = -fma(ca * ry, ry, cf);
                     const int i2 = 2 * it_i, j2 = 2 * it_j;
                     A[i2 * DP + j2] = a00; A[i2 * DP + j2 + 1] = a01;
@@ -540,7 +578,7 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                         double acc[kCH][2];
                         const int rb = rem / nchunk, ch = rem - rb * nchunk;
                         const int cb0 = ch * kCH, nch = min(kCH, NB - cb0);
-                        const double* Ap = Sw + a.off_AM + (8 * rb + g) * DP + t;      // A[row][k]
+                        const double* Ap = Sw + off_AM + (8 * rb + g) * DP + t;      // A[row][k]
                         const double* Bp = Sw + oJ + t * DP + 8 * cb0 + g;             // J[k][col]
                         dmma_chunk(D8, nch, [&](int k) { return Ap[k]; },
                                    [&](int c, int k) { return Bp[k * DP + 8 * c]; }, acc);
@@ -560,17 +598,17 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                             double* Sw = wbase + (size_t)w * wstride;
                             double acc0 = 0.0, acc1 = 0.0;
                             if (e < D) {
-                                const double* A = Sw + a.off_AM + e * DP;
+                                const double* A = Sw + off_AM + e * DP;
                                 const double* L = Sw + oL;
                                 for (int k = 0; k < D; k += 2) {
                                     const double2 av = *reinterpret_cast<const double2*>(A + k);
                                     const double2 lv = *reinterpret_cast<const double2*>(L + k);
                                     acc0 = fma(av.x, lv.x, acc0); acc1 = fma(av.y, lv.y, acc1);
                                 }
-                                (Sw + oK)[oL + e] = acc0 + acc1 + (Sw + a.off_kLx)[e];
+                                (Sw + oK)[oL + e] = acc0 + acc1 + (Sw + off_kLx)[e];
                             } else {
                                 const int c = e - D;
-                                const double* u = Sw + a.off_u;
+                                const double* u = Sw + off_u;
                                 const double* J = Sw + oJ + c;
                                 for (int k = 0; k < D; k += 2) {
                                     acc0 = fma(u[k], J[k * DP], acc0);
@@ -585,8 +623,8 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
                 // scalar rates: one warp per walker, shuffle reductions
                 for (int w = nwarp - 1 - warp; w < W && w >= 0; w += nwarp) {
                     double* Sw = wbase + (size_t)w * wstride;
-                    const double* part = Sw + a.off_part;
-                    const double* u = Sw + a.off_u; const double* L = Sw + oL;
+                    const double* part = Sw + off_part;
+                    const double* u = Sw + off_u; const double* L = Sw + oL;
                     double rho = 0.0, lp = 0.0;
                     for (int i = lane; i < n; i += 32) { rho += part[i]; lp += part[n + i]; }
                     for (int k = lane; k < D; k += 32) lp = fma(u[k], L[k], lp);
@@ -600,7 +638,7 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
             } else if (MODE >= MODE_DIV) {
                 for (int w = tid; w < W; w += T) {
                     double* Sw = wbase + (size_t)w * wstride;
-                    const double* part = Sw + a.off_part;
+                    const double* part = Sw + off_part;
                     double rho = 0.0;
                     for (int i = 0; i < n; ++i) rho += part[i];
                     (Sw + oK)[oDelta] = -rho;
@@ -684,5 +722,12 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) {
         if (MODE == MODE_ELOC) eloc_finale(a, base, wbase, pair_i, pair_j);
     }
 }
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) { flow_body<MODE, 0, 0>(a); }
+
+// Statically specialised E_loc sweep (one walker per CTA, two CTAs per SM).
+template <int SN, int SMU>
+__global__ void __launch_bounds__(256, 2) flow_kernel_eloc_static(const FlowArgs a) { flow_body<MODE_ELOC, SN, SMU>(a); }
 
 }  // namespace ff
