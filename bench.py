@@ -234,7 +234,10 @@ def run_ours(args):
         "roofline": {"bound": "fp64", "kernel": "ff::flow_kernel<MODE_ELOC>", "achieved": fl / (eloc_ms * 1e-3) / 1e12,
                      "peak": peak.value / 1e12, "unit": "TFLOP/s", "frac": fl / (eloc_ms * 1e-3) / peak.value,
                      "peak_source": "ff_fp64_peak DFMA microbenchmark on this device (MEASURED_PEAKS.json has no fp64 entry)",
-                     "traffic": None, "kernel_ms": eloc_ms,
+                     # ncu --set full (profiles/r01_eloc_ncu_full.md): 2.80 GB DRAM traffic for 8288 walkers
+                     "traffic": 2.80e9 / 8288 * B if (n == 20 and args.hidden == 50 and args.ode_steps == 16) else None,
+                     "traffic_source": "ncu dram__bytes_read+write, 8288-walker capture scaled per walker",
+                     "kernel_ms": eloc_ms,
                      "hbm": {"achieved": by / (eloc_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": by / (eloc_ms * 1e-3) / 1e9 / hbm_peak}},
         "energy": E,
