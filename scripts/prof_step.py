@@ -10,7 +10,7 @@ p.add_argument("--ode-steps", type=int, default=16)
 p.add_argument("--nup", type=int, default=10)
 p.add_argument("--ndown", type=int, default=10)
 a = p.parse_args()
-args = argparse.Namespace(hidden=50, ode_steps=a.ode_steps, nup=a.nup, ndown=a.ndown, Z=2.0)
+args = argparse.Namespace(hidden=int(os.environ.get("HID", "50")), ode_steps=a.ode_steps, nup=a.nup, ndown=a.ndown, Z=2.0)
 dev = torch.device("cuda:0")
 model = bench.build_model(args, dev)
 opt = torch.optim.Adam(model.parameters(), lr=1e-3)
