@@ -103,6 +103,7 @@ int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t
     a.W = W;
     threads = ((W * a.P + 31) / 32) * 32;
     if (threads < 64) threads = 64;
+    if (eloc && threads + 32 <= 256) threads += 32;      // helper warp: Gram matrix overlaps the MLP loop
     smem = (size_t)(common + (long long)W * a.wstride) * 8;
     return 0;
 }

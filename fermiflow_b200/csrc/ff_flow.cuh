@@ -166,11 +166,16 @@ __device__ __forceinline__ void gram_block_offsets(int blk, int W, int D8, int D
     oM = w * wstride + off_AM + (8 * rb + g) * DP + 8 * cb + 2 * t;
 }
 
-__device__ __forceinline__ GramPlan gram_plan(int W, int D8, int DP, int wstride, int oJ, int off_AM) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+// Blocks are dealt to the warps [warp0, warp0 + nwarp) only (helper warps when present).
+__device__ __forceinline__ GramPlan gram_plan(int W, int D8, int DP, int wstride, int oJ, int off_AM,
+                                              int warp0 = 0, int nwarp = -1) {
+    const int lane = threadIdx.x & 31;
+    if (nwarp < 0) nwarp = blockDim.x >> 5;
+    const int warp = (int)(threadIdx.x >> 5) - warp0;
     const int g = lane >> 2, t = lane & 3, NB = D8 >> 3, total = W * NB * (NB + 1) / 2;
     const int per = (total + nwarp - 1) / nwarp;
     GramPlan p;
+    if (warp < 0 || warp >= nwarp) { p.first = p.last = p.nch = 0; for (int c = 0; c < kCH; ++c) p.oA[c] = p.oB[c] = p.oM[c] = 0; return p; }
     p.first = min(total, warp * per);
     p.last = min(total, p.first + per);
     p.nch = min(kCH, p.last - p.first);
@@ -334,7 +339,9 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
     extern __shared__ __align__(16) double smem[];
     constexpr bool kS = SN > 0;
     constexpr FlowGeom GS = flow_geom(MODE, kS ? SN : 2, SMU != 0);
-    const int tid = threadIdx.x, T = kS ? GS.threads1 : (int)blockDim.x;
+    // one extra "helper" warp (when the launch provides it) computes the Gram matrix while the
+    // item warps are still in the MLP loop
+    const int tid = threadIdx.x, T = kS ? GS.threads1 + 32 : (int)blockDim.x;
     const int n = kS ? GS.n : a.n, D = kS ? GS.D : a.D, DP = kS ? GS.DP : a.DP, P = kS ? GS.P : a.P;
     const int NP = kS ? GS.NP : a.NP, W = kS ? 1 : a.W, NSV = kS ? GS.NSV : a.NSV;
     const int off_G = kS ? GS.off_G : a.off_G, off_AM = kS ? GS.off_AM : a.off_AM, off_u = kS ? GS.off_u : a.off_u;
@@ -376,7 +383,10 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
     const int oP3 = NSV, oP4 = NSV + NPAR, oPO = NSV + 2 * NPAR, oK = NSV + 3 * NPAR;
 
     GramPlan gplan;
-    if (MODE == MODE_ELOC) gplan = gram_plan(W, D8, DP, wstride, oJ, off_AM);
+    const int item_warps = (W * P + 31) >> 5;
+    const int helper_warps = (MODE == MODE_ELOC) ? nwarp - item_warps : 0;
+    if (MODE == MODE_ELOC) gplan = helper_warps > 0 ? gram_plan(W, D8, DP, wstride, oJ, off_AM, item_warps, helper_warps)
+                                                    : gram_plan(W, D8, DP, wstride, oJ, off_AM);
 
     // item owned by this thread
     const int it_w = tid / P, it_p = tid - it_w * P;
