@@ -522,26 +522,39 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
                         const int c = (MODE == MODE_ELOC) ? cc : (cc == 2 ? 6 : cc);   // logical quantity
                         const int gc = cc;                                             // column in the record
                         double accm = 0.0, accp = 0.0, accm2 = 0.0, accp2 = 0.0;
-                        {   // pairs (j, i), j < i : stored with r = y_j - y_i
-                            int idx = i - 1;                       // pair_index(0, i)
-                            int j = 0;
-                            for (; j + 2 <= i; j += 2) {
-                                const int idx2 = idx + n - j - 2;
-                                const double v0 = G[idx * GRg + gc], v1 = G[idx2 * GRg + gc];
-                                accm += v0; accm2 += v1;
-                                idx = idx2 + n - j - 3;
+                        if (kS) {
+                            // fixed trip count: every load of the particle's n-1 pair records is
+                            // independent of the others and issues back to back
+#pragma unroll
+                            for (int j = 0; j < (kS ? GS.n : 1); ++j) {
+                                const bool lower = j < i;
+                                const int idx = lower ? pair_index(j, i, n) : pair_index(i, j, n);
+                                const double v = (j == i) ? 0.0 : G[idx * GRg + gc];
+                                if (lower) { if (j & 1) accm2 += v; else accm += v; }
+                                else { if (j & 1) accp2 += v; else accp += v; }
                             }
-                            if (j < i) accm += G[idx * GRg + gc];
-                        }
-                        {   // pairs (i, j), j > i : consecutive
-                            const double* Gi = G + pair_index(i, i + 1, n) * GRg + gc;
-                            int j = i + 1;
-                            for (; j + 4 <= n; j += 4) {
-                                const double v0 = Gi[0], v1 = Gi[GRg], v2 = Gi[2 * GRg], v3 = Gi[3 * GRg];
-                                accp += v0; accp2 += v1; accp += v2; accp2 += v3;
-                                Gi += 4 * GRg;
+                        } else {
+                            {   // pairs (j, i), j < i : stored with r = y_j - y_i
+                                int idx = i - 1;                       // pair_index(0, i)
+                                int j = 0;
+                                for (; j + 2 <= i; j += 2) {
+                                    const int idx2 = idx + n - j - 2;
+                                    const double v0 = G[idx * GRg + gc], v1 = G[idx2 * GRg + gc];
+                                    accm += v0; accm2 += v1;
+                                    idx = idx2 + n - j - 3;
+                                }
+                                if (j < i) accm += G[idx * GRg + gc];
                             }
-                            for (; j < n; ++j) { accp += *Gi; Gi += GRg; }
+                            {   // pairs (i, j), j > i : consecutive
+                                const double* Gi = G + pair_index(i, i + 1, n) * GRg + gc;
+                                int j = i + 1;
+                                for (; j + 4 <= n; j += 4) {
+                                    const double v0 = Gi[0], v1 = Gi[GRg], v2 = Gi[2 * GRg], v3 = Gi[3 * GRg];
+                                    accp += v0; accp2 += v1; accp += v2; accp2 += v3;
+                                    Gi += 4 * GRg;
+                                }
+                                for (; j < n; ++j) { accp += *Gi; Gi += GRg; }
+                            }
                         }
                         accm += accm2; accp += accp2;
                         double acc = (c < 6) ? accp - accm : accp + accm;
