@@ -9,6 +9,7 @@
 #include "../../include/fermiflow_b200.h"
 #include "ff_adjoint.cuh"
 #include "ff_flow.cuh"
+#include "ff_eloc2.cuh"
 #include "ff_misc.cuh"
 
 namespace {
@@ -134,6 +135,35 @@ int launch_flow(ff::FlowArgs& a, int threads, size_t smem, cudaStream_t st) {
     return launch_flow_kernel(ff::flow_kernel<MODE>, a, threads, smem, st);
 }
 
+// Second-generation E_loc sweep (ff_eloc2.cuh): statically specialised per particle number.
+// Returns 1 when no specialisation covers the model (the caller falls back to flow_kernel).
+template <int SN, int SMU>
+int launch_eloc2(ff::FlowArgs& a, cudaStream_t st) {
+    constexpr ff::Eloc2Geom g = ff::eloc2_geom(SN, SMU != 0);
+    a.D = g.D; a.NP = g.NP; a.P = g.P; a.DP = g.DP; a.NV = g.NV; a.NSV = g.NSV; a.grec = ff::kGRec;
+    a.off_G = g.off_G; a.off_AM = g.off_AM; a.off_u = g.off_u; a.off_kLx = g.off_kLx; a.off_part = g.off_part;
+    a.off_x0 = g.off_x0; a.off_sl = g.off_sl; a.wstride = g.wstride; a.W = 1;
+    const int need = ff::slater_scratch_size(a.n_up, a.n - a.n_up) + 2 * g.D + g.n * g.n + g.NP + 8;
+    if (need > 2 * g.MAT) return fail(-2, "internal: finale scratch does not fit");
+    int common = ff::kTabDoubles + 6 * (ff::hpad2(a.H_eta) + ff::hpad2(a.H_mu));
+    common = even(common) + 2 * ((g.NP + 7) / 8) + 2;
+    const size_t smem = (size_t)(common + g.wstride) * 8;
+    if ((long long)smem > dev_info().smem_optin) return 1;
+    return launch_flow_kernel(ff::eloc2_kernel<SN, SMU>, a, g.threads, smem, st);
+}
+
+int try_eloc2(ff::FlowArgs& a, cudaStream_t st) {
+    // experimental (slower than flow_kernel_eloc_static at N = 20 so far): opt in with FF_ELOC_V2=1
+    if (getenv("FF_ELOC_V2") == nullptr) return 1;
+    if (a.H_mu > 0) {
+        switch (a.n) {
+            case 20: return launch_eloc2<20, 1>(a, st);
+            default: return 1;
+        }
+    }
+    return 1;
+}
+
 }  // namespace
 
 extern "C" {
@@ -193,6 +223,11 @@ int ff_eloc(const ff_model* m, const double* x, long long B, const int* orb, con
     a.stash_y = stash_y; a.stash_c = stash_c;
     a.orb = orb; a.walker_state = walker_state; a.Z = Z; a.harmonic = harmonic;
     a.logp = logp; a.grad = grad; a.lap = lap; a.kin = kinetic; a.pot = potential; a.eloc = eloc;
+    {
+        ff::FlowArgs a2 = a;
+        const int r = try_eloc2(a2, (cudaStream_t)stream);
+        if (r != 1) return r;
+    }
     return launch_flow<ff::MODE_ELOC>(a, threads, smem, (cudaStream_t)stream);
 }
 
