@@ -9,7 +9,9 @@
 #include "../../include/fermiflow_b200.h"
 #include "ff_adjoint.cuh"
 #include "ff_flow.cuh"
+#include "ff_flow_warp.cuh"
 #include "ff_eloc2.cuh"
+#include "ff_eloc3.cuh"
 #include "ff_misc.cuh"
 
 namespace {
@@ -126,41 +128,78 @@ int launch_flow_kernel(K kernel, ff::FlowArgs& a, int threads, size_t smem, cuda
     return 0;
 }
 
+// One-warp-per-walker sweeps (ff_flow_warp.cuh) when the pair items fill the lanes well.
+template <int MODE>
+int launch_flow_warp(ff::FlowArgs& a, cudaStream_t st) {
+    const DevInfo di = dev_info();
+    const ff::WarpFlowGeom wg = ff::warp_flow_geom(MODE, a.n, a.P);
+    const int warps = 8;
+    int common = ff::kTabDoubles + 6 * (((a.H_eta + 3) & ~3) + ((a.H_mu + 3) & ~3));
+    common = even(common) + 2 * ((a.NP + 7) / 8) + 2;
+    const size_t smem = (size_t)(common + (long long)warps * wg.slice) * 8;
+    if (smem > (size_t)di.smem_optin) return 1;
+    auto kernel = ff::flow_warp_kernel<MODE>;
+    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    int occ = 0;
+    FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * warps, smem));
+    if (occ < 1) return 1;
+    long long grid = std::min<long long>((a.B + warps - 1) / warps, (long long)di.sms * occ);
+    if (grid < 1) return 0;
+    kernel<<<(unsigned)grid, 32 * warps, smem, st>>>(a);
+    FF_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <int MODE>
 int launch_flow(ff::FlowArgs& a, int threads, size_t smem, cudaStream_t st) {
+    if constexpr (MODE != ff::MODE_ELOC) {
+        // lane efficiency of the warp-per-walker layout: NP pair items over ceil(NP / 32) rounds
+        const int rounds = (a.NP + 31) / 32;
+        if (a.NP > 0 && a.n <= 255 && 100 * a.NP >= 85 * 32 * rounds && getenv("FF_FLOW_CTA") == nullptr) {
+            const int r = launch_flow_warp<MODE>(a, st);
+            if (r != 1) return r;
+        }
+    }
     if (MODE == ff::MODE_ELOC && a.W == 1 && a.H_mu > 0 && getenv("FF_NO_STATIC") == nullptr) {
         // statically specialised sweeps for the benchmark sizes (BASELINE.json configs)
         if (a.n == 20) return launch_flow_kernel(ff::flow_kernel_eloc_static<20, 1>, a, threads, smem, st);
     }
+    if constexpr (MODE != ff::MODE_ELOC) {
+        if (threads <= 256 && getenv("FF_FLOW_BIG") == nullptr)
+            return launch_flow_kernel(ff::flow_kernel_small<MODE>, a, threads, smem, st);
+    }
     return launch_flow_kernel(ff::flow_kernel<MODE>, a, threads, smem, st);
 }
 
-// Second-generation E_loc sweep (ff_eloc2.cuh): statically specialised per particle number.
-// Returns 1 when no specialisation covers the model (the caller falls back to flow_kernel).
+// Warp-specialised two-walker pipeline (ff_eloc3.cuh): one CTA per SM.
 template <int SN, int SMU>
-int launch_eloc2(ff::FlowArgs& a, cudaStream_t st) {
-    constexpr ff::Eloc2Geom g = ff::eloc2_geom(SN, SMU != 0);
+int launch_eloc3(ff::FlowArgs& a, cudaStream_t st) {
+    constexpr ff::Eloc3Geom q = ff::eloc3_geom(SN, SMU != 0);
+    constexpr ff::Eloc2Geom g = q.g;
     a.D = g.D; a.NP = g.NP; a.P = g.P; a.DP = g.DP; a.NV = g.NV; a.NSV = g.NSV; a.grec = ff::kGRec;
     a.off_G = g.off_G; a.off_AM = g.off_AM; a.off_u = g.off_u; a.off_kLx = g.off_kLx; a.off_part = g.off_part;
     a.off_x0 = g.off_x0; a.off_sl = g.off_sl; a.wstride = g.wstride; a.W = 1;
     const int need = ff::slater_scratch_size(a.n_up, a.n - a.n_up) + 2 * g.D + g.n * g.n + g.NP + 8;
     if (need > 2 * g.MAT) return fail(-2, "internal: finale scratch does not fit");
-    int common = ff::kTabDoubles + 6 * (ff::hpad2(a.H_eta) + ff::hpad2(a.H_mu));
-    common = even(common) + 2 * ((g.NP + 7) / 8) + 2;
-    const size_t smem = (size_t)(common + g.wstride) * 8;
-    if ((long long)smem > dev_info().smem_optin) return 1;
-    return launch_flow_kernel(ff::eloc2_kernel<SN, SMU>, a, g.threads, smem, st);
+    constexpr int NI = FF_ELOC3_ILP;
+    const int common = ff::kTabDoubles + 12 * (ff::half_rows<NI>(a.H_eta) + ff::half_rows<NI>(a.H_mu)) + 2 * ((g.NP + 7) / 8) + 4;
+    const size_t smem = (size_t)(common + 2 * g.wstride) * 8;
+    const DevInfo di = dev_info();
+    if ((long long)smem > di.smem_optin || q.threads > 1024) return 1;
+    auto kernel = ff::eloc3_kernel<SN, SMU>;
+    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = (a.B + 1) / 2;
+    if (grid > di.sms) grid = di.sms;
+    if (grid < 1) return 0;
+    kernel<<<(unsigned)grid, q.threads, smem, st>>>(a);
+    FF_CUDA(cudaGetLastError());
+    return 0;
 }
 
-int try_eloc2(ff::FlowArgs& a, cudaStream_t st) {
-    // experimental (slower than flow_kernel_eloc_static at N = 20 so far): opt in with FF_ELOC_V2=1
-    if (getenv("FF_ELOC_V2") == nullptr) return 1;
-    if (a.H_mu > 0) {
-        switch (a.n) {
-            case 20: return launch_eloc2<20, 1>(a, st);
-            default: return 1;
-        }
-    }
+// Opt-in (FF_ELOC_V3=1): 189 ms against 177 ms of flow_kernel_eloc_static at N = 20, 65536 walkers.
+int try_eloc_pipeline(ff::FlowArgs& a, cudaStream_t st) {
+    if (getenv("FF_ELOC_V3") != nullptr && a.H_mu > 0 && a.n == 20) return launch_eloc3<20, 1>(a, st);
     return 1;
 }
 
@@ -225,7 +264,7 @@ int ff_eloc(const ff_model* m, const double* x, long long B, const int* orb, con
     a.logp = logp; a.grad = grad; a.lap = lap; a.kin = kinetic; a.pot = potential; a.eloc = eloc;
     {
         ff::FlowArgs a2 = a;
-        const int r = try_eloc2(a2, (cudaStream_t)stream);
+        const int r = try_eloc_pipeline(a2, (cudaStream_t)stream);
         if (r != 1) return r;
     }
     return launch_flow<ff::MODE_ELOC>(a, threads, smem, (cudaStream_t)stream);

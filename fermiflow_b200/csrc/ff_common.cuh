@@ -52,10 +52,13 @@ __device__ __forceinline__ void fill_exp_table(double* tab) {
 
 // exp() range-reduction constants, read through the constant bank so that ptxas folds them
 // into DFMA operands instead of re-materialising 64-bit immediates inside the hot loop.
+// [3..6]: degree-5 polynomial of exp(r) on |r| <= ln2/64 -- the degree-6 Taylor polynomial with its
+// r^6 term economised onto Chebyshev T6 (max relative error 1.4e-16):
+//   exp(r) ~ 1 + r + c2 r^2 + r^3/6 + c4 r^4 + r^5/120,  c2 = 1/2 - a^4/1280,  c4 = 1/24 + a^2/480.
 __constant__ double c_sig[8] = {46.16624130844683,        // 32 / ln 2
                                 0.02166084938653512,      // ln2/32, low 21 mantissa bits zero
                                 5.9631716539705866e-12,   // ln2/32 remainder
-                                1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.0};
+                                1.0 / 120.0, 0.04166691103770646, 1.0 / 6.0, 0.4999999999892509, 0.0};
 
 __device__ __forceinline__ double rcp_approx(double x) {
     double y;
@@ -63,9 +66,16 @@ __device__ __forceinline__ double rcp_approx(double x) {
     return y;
 }
 
-// Logistic sigmoid 1 / (1 + exp(-u)) in fp64 with 15 FP64-pipe instructions:
-//   exp(-u) = 2^m * 2^(j/32) * exp(r), |r| <= ln2/64, degree-6 Taylor (remainder 3.5e-18),
-//   reciprocal = MUFU.RCP64H seed + one cubic Newton step.
+// 2^m * T for a table value T in [1, 2): the exponent is added in the integer pipe, off the FP64
+// critical path (m is clamped so that the result stays a normal number).
+__device__ __forceinline__ double scale_pow2(double T, int k) {
+    const int m = min(max(k >> 5, -1020), 1020);
+    return __hiloint2double(__double2hiint(T) + (m << 20), __double2loint(T));
+}
+
+// Logistic sigmoid 1 / (1 + exp(-u)) in fp64 with 13 FP64-pipe instructions:
+//   exp(-u) = 2^m * 2^(j/32) * exp(r), |r| <= ln2/64, degree-5 economised polynomial,
+//   1 + exp(-u) = fma(exp(r), 2^m 2^(j/32), 1), reciprocal = MUFU.RCP64H seed + one cubic Newton step.
 // `tabl` = shared exp table + (lane & 15).  Valid for |u| < 2^25 (saturates correctly for
 // |u| > 709); relative error a few ulp.  Matches torch.sigmoid (MLP.py:17) to ~4e-16.
 __device__ __forceinline__ double sigmoid_fast(double u, const double* __restrict__ tabl) {
@@ -74,51 +84,25 @@ __device__ __forceinline__ double sigmoid_fast(double u, const double* __restric
     const double kf = t - MAGIC;                        // k = rint(-u * 32/ln2)
     double r = fma(kf, -c_sig[1], -u);
     r = fma(kf, -c_sig[2], r);                          // r = -u - k ln2/32
+    const int k = __double2loint(t);
+    const double T = scale_pow2(tabl[(k & 31) << 4], k);
     double p = fma(r, c_sig[3], c_sig[4]);
     p = fma(p, r, c_sig[5]);
     p = fma(p, r, c_sig[6]);
-    p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);                                 // exp(r)
-    const int k = __double2loint(t);
-    const int m = min(max(k >> 5, -1020), 1020);
-    double e = p * tabl[(k & 31) << 4];
-    e = __hiloint2double(__double2hiint(e) + (m << 20), __double2loint(e));   // * 2^m
-    const double den = 1.0 + e;
+    const double den = fma(p, T, 1.0);
     const double y = rcp_approx(den);
     double q = fma(-den, y, 1.0);
     q = fma(q, q, q);
     return fma(y, q, y);
 }
 
-// Two independent sigmoids in lock-step (explicit ILP 2: the FP64 pipe issues one warp
-// instruction every 2 cycles and each chain is ~14 dependent FP64 ops deep).
+// Two independent sigmoids in lock-step.
 __device__ __forceinline__ void sigmoid_fast2(double u0, double u1, const double* __restrict__ tabl,
                                               double& s0, double& s1) {
-    const double MAGIC = 6755399441055744.0;
-    const double L = c_sig[0], C_HI = c_sig[1], C_LO = c_sig[2];
-    double t0 = fma(u0, -L, MAGIC), t1 = fma(u1, -L, MAGIC);
-    double k0 = t0 - MAGIC, k1 = t1 - MAGIC;
-    double r0 = fma(k0, -C_HI, -u0), r1 = fma(k1, -C_HI, -u1);
-    r0 = fma(k0, -C_LO, r0); r1 = fma(k1, -C_LO, r1);
-    const int i0 = __double2loint(t0), i1 = __double2loint(t1);
-    const double T0 = tabl[(i0 & 31) << 4], T1 = tabl[(i1 & 31) << 4];
-    const double c6 = c_sig[3], c5 = c_sig[4], c4 = c_sig[5], c3 = c_sig[6];
-    double p0 = fma(r0, c6, c5), p1 = fma(r1, c6, c5);
-    p0 = fma(p0, r0, c4); p1 = fma(p1, r1, c4);
-    p0 = fma(p0, r0, c3); p1 = fma(p1, r1, c3);
-    p0 = fma(p0, r0, 0.5); p1 = fma(p1, r1, 0.5);
-    p0 = fma(p0, r0, 1.0); p1 = fma(p1, r1, 1.0);
-    p0 = fma(p0, r0, 1.0); p1 = fma(p1, r1, 1.0);
-    const int m0 = min(max(i0 >> 5, -1020), 1020), m1 = min(max(i1 >> 5, -1020), 1020);
-    double e0 = p0 * T0, e1 = p1 * T1;
-    e0 = __hiloint2double(__double2hiint(e0) + (m0 << 20), __double2loint(e0));
-    e1 = __hiloint2double(__double2hiint(e1) + (m1 << 20), __double2loint(e1));
-    const double d0 = 1.0 + e0, d1 = 1.0 + e1;
-    const double y0 = rcp_approx(d0), y1 = rcp_approx(d1);
-    double q0 = fma(-d0, y0, 1.0), q1 = fma(-d1, y1, 1.0);
-    q0 = fma(q0, q0, q0); q1 = fma(q1, q1, q1);
-    s0 = fma(y0, q0, y0); s1 = fma(y1, q1, y1);
+    s0 = sigmoid_fast(u0, tabl);
+    s1 = sigmoid_fast(u1, tabl);
 }
 
 // N sigmoids in lock-step (all loops fully unrolled, arrays live in registers).
@@ -126,8 +110,8 @@ template <int N>
 __device__ __forceinline__ void sigmoid_fastN(const double (&u)[N], const double* __restrict__ tabl, double (&s)[N]) {
     const double MAGIC = 6755399441055744.0;
     const double L = c_sig[0], C_HI = c_sig[1], C_LO = c_sig[2];
-    const double c6 = c_sig[3], c5 = c_sig[4], c4 = c_sig[5], c3 = c_sig[6];
-    double t[N], r[N], p[N], T[N], e[N], dn[N], y[N], q[N];
+    const double c5 = c_sig[3], c4 = c_sig[4], c3 = c_sig[5], c2 = c_sig[6];
+    double t[N], r[N], p[N], T[N], dn[N], y[N], q[N];
     int ik[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) t[i] = fma(u[i], -L, MAGIC);
@@ -136,27 +120,19 @@ __device__ __forceinline__ void sigmoid_fastN(const double (&u)[N], const double
 #pragma unroll
     for (int i = 0; i < N; ++i) r[i] = fma(t[i], -C_HI, -u[i]);
 #pragma unroll
-    for (int i = 0; i < N; ++i) { r[i] = fma(t[i], -C_LO, r[i]); T[i] = tabl[(ik[i] & 31) << 4]; }
+    for (int i = 0; i < N; ++i) { r[i] = fma(t[i], -C_LO, r[i]); T[i] = scale_pow2(tabl[(ik[i] & 31) << 4], ik[i]); }
 #pragma unroll
-    for (int i = 0; i < N; ++i) p[i] = fma(r[i], c6, c5);
-#pragma unroll
-    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], c4);
+    for (int i = 0; i < N; ++i) p[i] = fma(r[i], c5, c4);
 #pragma unroll
     for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], c3);
 #pragma unroll
-    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], 0.5);
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], c2);
 #pragma unroll
     for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], 1.0);
 #pragma unroll
     for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], 1.0);
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const int m = min(max(ik[i] >> 5, -1020), 1020);
-        e[i] = p[i] * T[i];
-        e[i] = __hiloint2double(__double2hiint(e[i]) + (m << 20), __double2loint(e[i]));
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) { dn[i] = 1.0 + e[i]; y[i] = rcp_approx(dn[i]); }
+    for (int i = 0; i < N; ++i) { dn[i] = fma(p[i], T[i], 1.0); y[i] = rcp_approx(dn[i]); }
 #pragma unroll
     for (int i = 0; i < N; ++i) q[i] = fma(-dn[i], y[i], 1.0);
 #pragma unroll

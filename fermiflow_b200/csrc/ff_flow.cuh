@@ -215,9 +215,11 @@ __device__ __forceinline__ void gram_run(const GramPlan& p, int W, int D8, int D
 // Hessian contraction <H0, J J^T>, then assemble
 //   log p = log p0 - Delta,  grad = J^T g0 - gDelta,  lap = <H0, JJ^T> + g0.L - lapDelta,
 //   E_loc = -1/4 lap - 1/8 |grad|^2 + V(x)                       (VMC.py:48-55).
+template <class Team = CtaTeam>
 __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
-                            const unsigned char* pair_i, const unsigned char* pair_j) {
-    const int tid = threadIdx.x, T = blockDim.x;
+                            const unsigned char* pair_i, const unsigned char* pair_j, Team team = Team(),
+                            int team_warp0 = 0) {
+    const int tid = team.tid(), T = team.size();
     const int n = a.n, D = a.D, DP = a.DP, W = a.W, NP = a.NP;
     const int oL = D, oG = 2 * D, oS = 3 * D, oJ = 3 * D + 2;
     auto S_in = [&](int w) { return wbase + (size_t)w * a.wstride; };
@@ -230,11 +232,11 @@ __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
     slater_team<true>(W, n, a.n_up,
         [&](int w) { return (const double*)S_in(w); }, scr,
         [&](int w) { long long b = base + w; int row = (a.walker_state && b < a.B) ? a.walker_state[b] : 0;
-                     return a.orb + (size_t)row * n; });
+                     return a.orb + (size_t)row * n; }, team);
 
     // M = J J^T at the end point (upper block triangle), into the AM buffer
     {
-        const GramPlan gp = gram_plan(W, (D + 7) & ~7, DP, a.wstride, oJ, a.off_AM);
+        const GramPlan gp = gram_plan(W, (D + 7) & ~7, DP, a.wstride, oJ, a.off_AM, team_warp0, T >> 5);
         gram_run(gp, W, (D + 7) & ~7, DP, wbase, a.wstride, oJ, a.off_AM);
     }
     // g0 and the per-(i,j) Hessian contraction terms
@@ -248,7 +250,7 @@ __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
             g0p(w)[2 * (blk.i0 + i) + 1] = 2.0 * S[blk.by() + i * ns + i];
         }
     }
-    __syncthreads();
+    team.sync();
     for (int g = tid; g < W * n * n; g += T) {
         int w = g / (n * n), rem = g - w * n * n;
         int I = rem / n, Jp = rem - I * n;
@@ -285,7 +287,7 @@ __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
         const double dx = x0[2 * i] - x0[2 * j], dy = x0[2 * i + 1] - x0[2 * j + 1];
         red(w)[n * n + p] = a.Z / sqrt(fma(dx, dx, dy * dy));
     }
-    __syncthreads();
+    team.sync();
     // grad[c] = sum_r g0[r] J[r][c] - gDelta[c]   (kept in the KK area is dead: write to P3 slot 0..D)
     for (int g = tid; g < W * D; g += T) {
         int w = g / D, c = g - w * D;
@@ -297,7 +299,7 @@ __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
         long long b = base + w;
         if (b < a.B && a.grad) a.grad[b * D + c] = acc;
     }
-    __syncthreads();
+    team.sync();
     for (int w = tid; w < W; w += T) {
         long long b = base + w;
         if (b >= a.B) continue;
@@ -328,7 +330,7 @@ __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
         if (a.pot) a.pot[b] = pot;
         if (a.eloc) a.eloc[b] = kin + pot;
     }
-    __syncthreads();
+    team.sync();
 }
 
 // SN > 0 fixes the particle number (and SMU the presence of the one-body MLP) at compile time:
@@ -748,6 +750,11 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
 
 template <int MODE>
 __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) { flow_body<MODE, 0, 0>(a); }
+
+// Same body for CTAs of at most 256 threads, capped at 64 registers: four CTAs (32 warps) per SM
+// keep the FP64 pipe fed across the per-stage barriers of the value / divergence sweeps.
+template <int MODE>
+__global__ void __launch_bounds__(256, 4) flow_kernel_small(const FlowArgs a) { flow_body<MODE, 0, 0>(a); }
 
 // Statically specialised E_loc sweep (one walker per CTA, two CTAs per SM).
 template <int SN, int SMU>

@@ -11,6 +11,20 @@
 
 namespace ff {
 
+// A team is the set of threads that runs a cooperative routine: the whole CTA (CtaTeam) or a
+// subset of its warps synchronising on a named barrier (SubTeam; warp-specialised kernels).
+struct CtaTeam {
+    __device__ __forceinline__ int tid() const { return threadIdx.x; }
+    __device__ __forceinline__ int size() const { return blockDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+struct SubTeam {
+    int t, T, bar;          // index inside the team, team size (multiple of 32), barrier id (1..15)
+    __device__ __forceinline__ int tid() const { return t; }
+    __device__ __forceinline__ int size() const { return T; }
+    __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(T) : "memory"); }
+};
+
 // scratch layout of one spin block with ns particles (doubles)
 struct SlBlk {
     int ns, i0, base;
@@ -42,9 +56,9 @@ __device__ __forceinline__ SlBlk slater_blk(int s, int n, int n_up) {
 // B^x, B^y, C.  On return, for spin block s of walker w (scratch pointer S = sptr(w)):
 //   S[blk.misc()+2] = log|det Phi|, S[blk.aug() + i*2ns + ns + j] = Phi^-1[i][j].
 // All threads of the CTA must call it.  DERIV = false stops after log|det|.
-template <bool DERIV, class ZPtr, class SPtr, class OrbPtr>
-__device__ void slater_team(int W, int n, int n_up, ZPtr zptr, SPtr sptr, OrbPtr orbptr) {
-    const int tid = threadIdx.x, T = blockDim.x;
+template <bool DERIV, class ZPtr, class SPtr, class OrbPtr, class Team = CtaTeam>
+__device__ void slater_team(int W, int n, int n_up, ZPtr zptr, SPtr sptr, OrbPtr orbptr, Team team = Team()) {
+    const int tid = team.tid(), T = team.size();
     const double inv_sqrt_pi = 0.56418958354775628695;
     // ---- F1: matrices ------------------------------------------------------------------
     for (int s = 0; s < 2; ++s) {
@@ -72,7 +86,7 @@ __device__ void slater_team(int W, int n, int n_up, ZPtr zptr, SPtr sptr, OrbPtr
         }
         for (int w = tid; w < W; w += T) sptr(w)[blk.misc() + 2] = 0.0;
     }
-    __syncthreads();
+    team.sync();
     // ---- F2: Gauss-Jordan on [Phi | I] ---------------------------------------------------
     const int nmax = max(n_up, n - n_up);
     for (int k = 0; k < nmax; ++k) {
@@ -92,7 +106,7 @@ __device__ void slater_team(int W, int n, int n_up, ZPtr zptr, SPtr sptr, OrbPtr
             S[blk.misc() + 1] = A[p * 2 * ns + k];
             S[blk.misc() + 2] += log(best);
         }
-        __syncthreads();
+        team.sync();
         for (int s = 0; s < 2; ++s) {                    // swap rows k <-> p, scale row k
             const SlBlk blk = slater_blk(s, n, n_up);
             const int ns = blk.ns;
@@ -108,7 +122,7 @@ __device__ void slater_team(int W, int n, int n_up, ZPtr zptr, SPtr sptr, OrbPtr
                 A[k * 2 * ns + c] = vp * ipv;
             }
         }
-        __syncthreads();
+        team.sync();
         for (int s = 0; s < 2; ++s) {                    // save multipliers (column k)
             const SlBlk blk = slater_blk(s, n, n_up);
             const int ns = blk.ns;
@@ -119,7 +133,7 @@ __device__ void slater_team(int W, int n, int n_up, ZPtr zptr, SPtr sptr, OrbPtr
                 S[blk.col() + r] = (r == k) ? 0.0 : S[blk.aug() + r * 2 * ns + k];
             }
         }
-        __syncthreads();
+        team.sync();
         for (int s = 0; s < 2; ++s) {                    // eliminate
             const SlBlk blk = slater_blk(s, n, n_up);
             const int ns = blk.ns;
@@ -132,7 +146,7 @@ __device__ void slater_team(int W, int n, int n_up, ZPtr zptr, SPtr sptr, OrbPtr
                 A[r * 2 * ns + c] = fma(-S[blk.col() + r], A[k * 2 * ns + c], A[r * 2 * ns + c]);
             }
         }
-        __syncthreads();
+        team.sync();
     }
     if (!DERIV) return;
     // ---- F3: B^x, B^y, C ---------------------------------------------------------------
@@ -173,7 +187,7 @@ __device__ void slater_team(int W, int n, int n_up, ZPtr zptr, SPtr sptr, OrbPtr
             }
         }
     }
-    __syncthreads();
+    team.sync();
 }
 
 }  // namespace ff

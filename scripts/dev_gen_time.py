@@ -1,0 +1,19 @@
+"""generate / delta_logp kernel times at N = 20 (CUDA events)."""
+import os, sys, argparse
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, bench
+torch.set_default_dtype(torch.float64)
+dev = torch.device("cuda:0")
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+args = argparse.Namespace(hidden=50, ode_steps=16, nup=10, ndown=10, Z=2.0)
+model = bench.build_model(args, dev)
+z = model.basedist.sample(model.orbitals_up, model.orbitals_down, (B,))
+def t(f):
+    f(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for _ in range(3):
+        e0.record(); f(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    return min(ts)
+x = model.cnf.generate(z)
+print("generate %.1f ms   delta_logp %.1f ms" % (t(lambda: model.cnf.generate(z)), t(lambda: model.cnf.delta_logp(x))))

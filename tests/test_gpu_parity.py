@@ -339,3 +339,108 @@ def test_flow_reversibility_full_size(dev):
     assert (zb - z).abs().max() < 1e-4          # RK4 truncation error (close pairs: |r| cone)
     assert (zb - z).abs().mean() < 1e-5
     assert torch.isfinite(dl).all()
+
+
+# ---------------------------------------------------------------------------------------
+# Kernel variants: every specialised kernel must agree with the oracle / the generic kernel.
+
+def _env(**kw):
+    import contextlib, os
+
+    @contextlib.contextmanager
+    def cm():
+        old = {k: os.environ.get(k) for k in kw}
+        try:
+            for k, v in kw.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+            yield
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    return cm()
+
+
+def test_warp_per_walker_flow_vs_oracle(dev, O):
+    """N = 14 (91 pair items fill 95 % of three lane rounds) runs the one-warp-per-walker
+    kernels (ff_flow_warp.cuh): generate, delta_logp and the stashing sweep + backward against
+    the oracle's fixed-step RK4 and autograd."""
+    from fermiflow_b200 import Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
+    nup = ndn = 7
+    n, S, B = 14, 4, 6
+    eta, mu = rand_mlp(9, 11, 0.05, dev), rand_mlp(7, 12, 0.05, dev)
+    ts = (0.0, 1.0)
+    cnf = CNF(Backflow(eta, mu=mu), ts, nsteps=S)
+    gen = torch.Generator().manual_seed(3)
+    z0 = 0.9 * torch.randn(B, n, 2, generator=gen)
+    eta_c, mu_c = cpu_params(eta), cpu_params(mu)
+    x = cnf.generate(z0.to(dev))
+    x_ref = O.cnf_generate(z0, eta_c, mu_c, ts, S)
+    close(x, x_ref, 1e-12)
+    z, dl = cnf.delta_logp(x)
+    z_ref, dl_ref = O.cnf_delta_logp(x_ref, eta_c, mu_c, ts, S)
+    close(z, z_ref, 1e-12)
+    close(dl, dl_ref, 1e-11, 1e-13)
+    # no one-body term
+    cnf2 = CNF(Backflow(eta), ts, nsteps=S)
+    close(cnf2.generate(z0.to(dev)), O.cnf_generate(z0, eta_c, None, ts, S), 1e-12)
+    # stash + exact reverse mode: d logp / d params against autograd through the oracle
+    model = GSVMC(nup, ndn, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(2.0), sp_potential=HO()).to(dev)
+    w = torch.randn(B, generator=gen) / B
+    up, dn = list(range(nup)), list(range(ndn))
+    gref = O.weighted_logp_param_grad(x_ref, w, up, dn, eta_c, mu_c, ts, S)
+    lp = model.logp(x.clone().requires_grad_(True), params_require_grad=True)
+    close(lp, O.logp(x_ref, up, dn, eta_c, mu_c, ts, S))
+    (lp * w.to(dev)).sum().backward()
+    names = [eta.fc1.weight, eta.fc1.bias, eta.fc2.weight, mu.fc1.weight, mu.fc1.bias, mu.fc2.weight]
+    for p, gr in zip(names, gref):
+        close(p.grad.reshape(-1), gr.reshape(-1), 1e-9, 1e-13)
+
+
+def _n20_model(dev, nsteps=8, H=50):
+    from fermiflow_b200 import Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
+    eta, mu = rand_mlp(H, 21, 0.02, dev), rand_mlp(H, 22, 0.02, dev)
+    cnf = CNF(Backflow(eta, mu=mu), (0.0, 1.0), nsteps=nsteps)
+    return GSVMC(10, 10, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(2.0), sp_potential=HO()).to(dev)
+
+
+def test_flow_kernel_variants_agree_full_size(dev):
+    """N = 20: one-warp-per-walker sweeps against the CTA-synchronous flow_kernel (FF_FLOW_CTA=1)
+    and its 128-register build (FF_FLOW_BIG=1) on the same walkers."""
+    model = _n20_model(dev)
+    z, _ = model.sample((777,))
+    outs = []
+    for env in (dict(FF_FLOW_CTA=None, FF_FLOW_BIG=None), dict(FF_FLOW_CTA="1", FF_FLOW_BIG=None),
+                dict(FF_FLOW_CTA="1", FF_FLOW_BIG="1")):
+        with _env(**env):
+            x = model.cnf.generate(z)
+            zz, dl = model.cnf.delta_logp(x)
+            outs.append((x, zz, dl))
+    for o in outs[1:]:
+        close(o[0], outs[0][0], 1e-13)
+        close(o[1], outs[0][1], 1e-13)
+        close(o[2], outs[0][2], 1e-12, 1e-14)
+
+
+@pytest.mark.parametrize("B", [1, 2, 297, 1500])
+def test_eloc_kernel_variants_agree_full_size(dev, B):
+    """N = 20: the statically specialised sweep (default), the generic flow_kernel<MODE_ELOC>
+    (FF_NO_STATIC=1, the one pinned against the oracle at small N) and the warp-specialised
+    two-walker pipeline (FF_ELOC_V3=1; odd walker counts exercise its slot shutdown)."""
+    model = _n20_model(dev, nsteps=4)
+    _, x = model.sample((B,))
+    res = []
+    for env in (dict(FF_NO_STATIC=None, FF_ELOC_V3=None), dict(FF_NO_STATIC="1", FF_ELOC_V3=None),
+                dict(FF_NO_STATIC=None, FF_ELOC_V3="1")):
+        with _env(**env):
+            res.append(model.local_energy(x, stash=True))
+    for r in res[1:]:
+        for k in ("z", "logp", "grad", "lap", "kinetic", "potential", "eloc"):
+            close(getattr(r, k), getattr(res[0], k), 1e-11, 1e-12)
+        close(r.stash.y, res[0].stash.y, 1e-13)
+        close(r.stash.c, res[0].stash.c, 1e-12, 1e-14)
