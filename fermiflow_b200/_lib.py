@@ -33,6 +33,7 @@ SIGNATURES = {
     "ff_stash_sizes": ([_M, _LL, C.POINTER(_LL), C.POINTER(_LL)], C.c_int),
     "ff_slater_logabsdet": ([_P, _LL, _I, _P, _P, _P, _P, _P, _P], C.c_int),
     "ff_free_fermion_logp": ([_P, _LL, _I, _I, _P, _P, _P, _P, _P], C.c_int),
+    "ff_free_fermion_logp_lap": ([_P, _LL, _I, _I, _P, _P, _P, _P, _P, _P], C.c_int),
     "ff_metropolis": ([_LL, _I, _I, _P, _P, _I, _D, C.c_ulonglong, _LL, _P, _P, _P, _P, _P, _P], C.c_int),
     "ff_eloc": ([_M, _P, _LL, _P, _P, _D, _I] + [_P] * 10 + [_P], C.c_int),
     "ff_logp_backward": ([_M, _LL] + [_P] * 12 + [_P], C.c_int),

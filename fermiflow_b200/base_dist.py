@@ -52,6 +52,21 @@ class FreeFermion(BaseDist):
         orb = orbital_indices(tuple(orbitals_up) + tuple(orbitals_down), x.device)
         return _FreeFermionLogp.apply(x, orb, None, len(orbitals_up), len(orbitals_down))
 
+    def log_prob_grad_laplacian(self, orbitals_up, orbitals_down, x):
+        """log p0(x), grad and Laplacian in one fused kernel (C ABI ff_free_fermion_logp_lap):
+        what utils.py:44-65 y_grad_laplacian(self.log_prob, x) returns through 1 + 2N autograd
+        passes in the reference."""
+        n_up, n_dn = len(orbitals_up), len(orbitals_down)
+        orb = orbital_indices(tuple(orbitals_up) + tuple(orbitals_down), x.device)
+        xf = x.detach().reshape(-1, n_up + n_dn, 2).contiguous()
+        B = xf.shape[0]
+        logp = torch.empty(B, dtype=xf.dtype, device=xf.device)
+        grad, lap = torch.empty_like(xf), torch.empty_like(logp)
+        L.check(L.lib().ff_free_fermion_logp_lap(L.ptr(xf), B, n_up, n_dn, L.ptr(orb, torch.int32), None,
+                                                 L.ptr(logp), L.ptr(grad), L.ptr(lap), L.stream()))
+        bs = x.shape[:-2]
+        return logp.reshape(bs), grad.reshape(x.shape), lap.reshape(bs)
+
     def _metropolis(self, B, n_up, n_dn, orb, walker_state, steps, tau, noise=None):
         x = torch.empty(B, n_up + n_dn, 2, dtype=torch.float64, device=self.device)
         x0 = nrm = uni = None

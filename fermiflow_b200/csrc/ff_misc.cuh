@@ -161,6 +161,138 @@ __global__ void __launch_bounds__(256) slater_kernel(const SlaterArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// The same with ONE WARP PER WALKER (spin blocks of at most 16 particles): no CTA barrier.
+//   1. lanes = (particle, coordinate): all eight 1D oscillator functions psi_a, psi_a', psi_a''
+//      by the three-term recursion with tabulated square roots                    (orbitals.py:66-90)
+//   2. Phi_ik = psi_nx(k)(x_i) psi_ny(k)(y_i) / sqrt(pi) into [Phi | I]; lanes = columns of the
+//      augmented matrix run Gauss-Jordan with partial pivoting (warp arg-max by shuffles)
+//   3. lanes = particles: B^x_ii, B^y_ii, C^xx_i, C^yy_i = sum_k d Phi_ik Phi^-1_ki from the 1D
+//      table; gradient 2 B (Jacobi's formula), Laplacian sum_i C^xx + C^yy - B^x^2 - B^y^2.
+// Replaces slater.py:4-68 / 70-156 forward + backward and the 2N autograd passes of
+// utils.py:44-65 for f = FreeFermion.log_prob.
+// ---------------------------------------------------------------------------------------
+__constant__ double c_herm_up[8] = {   // sqrt(2 / (k + 1))
+    1.4142135623730951, 1.0, 0.8164965809277260, 0.7071067811865476, 0.6324555320336759,
+    0.5773502691896257, 0.5345224838248488, 0.5};
+__constant__ double c_herm_dn[8] = {   // sqrt(k / (k + 1))
+    0.0, 0.7071067811865476, 0.8164965809277260, 0.8660254037844386, 0.8944271909999159,
+    0.9128709291752769, 0.9258200997725514, 0.9354143466934853};
+__constant__ double c_herm_d1[8] = {   // sqrt(2 a)
+    0.0, 1.4142135623730951, 2.0, 2.4494897427831779, 2.8284271247461903, 3.1622776601683795,
+    3.4641016151377544, 3.7416573867739413};
+
+constexpr int kSlaterWarpMax = 16;          // particles per spin block
+constexpr int kHermStride = 49;             // doubles per particle in the 1D table (odd: no bank conflicts)
+__host__ __device__ inline int slater_warp_slice(int nmax) {      // doubles of shared memory per warp
+    return ff_even(nmax * (2 * nmax + 1) + nmax * kHermStride + 2);
+}
+
+__global__ void __launch_bounds__(256) slater_warp_kernel(const SlaterArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int n = a.n, D = 2 * n;
+    const int nmax = max(a.n_up, n - a.n_up);
+    double* A = smem + (size_t)warp * slater_warp_slice(nmax);        // [ns][2 ns + 1]
+    double* Ht = A + nmax * (2 * nmax + 1);                            // [ns][kHermStride]: (coord, order, deriv)
+    const double inv_sqrt_pi = 0.56418958354775628695;
+    const bool deriv = a.grad != nullptr || a.lap != nullptr;
+    const long long wstride = (long long)gridDim.x * nwarp;
+    for (long long b = (long long)blockIdx.x * nwarp + warp; b < a.B; b += wstride) {
+        const int* orb = a.orb + (size_t)(a.walker_state ? a.walker_state[b] : 0) * n;
+        double logdet = 0.0, lap = 0.0;
+        for (int s = 0; s < 2; ++s) {
+            const int ns = s ? n - a.n_up : a.n_up, i0 = s ? a.n_up : 0;
+            if (ns == 0) continue;
+            const int LD = 2 * ns + 1;
+            // ---- 1. 1D oscillator functions --------------------------------------------------
+            for (int e = lane; e < 2 * ns; e += 32) {
+                const int i = e >> 1, c = e & 1;
+                const double x = a.x[b * D + 2 * (i0 + i) + c];
+                const double g = exp(-0.5 * x * x);
+                double* t = Ht + i * kHermStride + c * 24;
+                double hm = 0.0, hh = 1.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    t[3 * k] = hh * g;
+                    t[3 * k + 1] = (c_herm_d1[k] * hm - x * hh) * g;
+                    t[3 * k + 2] = (x * x - (2.0 * k + 1.0)) * hh * g;
+                    const double hn = c_herm_up[k] * x * hh - c_herm_dn[k] * hm;
+                    hm = hh; hh = hn;
+                }
+            }
+            __syncwarp();
+            // ---- 2. [Phi | I], Gauss-Jordan ----------------------------------------------------
+            for (int e = lane; e < ns * ns; e += 32) {
+                const int i = e / ns, k = e - i * ns;
+                const int id = orb[i0 + k];
+                const double* t = Ht + i * kHermStride;
+                A[i * LD + k] = inv_sqrt_pi * t[3 * c_orb_nx[id]] * t[24 + 3 * c_orb_ny[id]];
+                A[i * LD + ns + k] = (i == k) ? 1.0 : 0.0;
+            }
+            __syncwarp();
+            for (int k = 0; k < ns; ++k) {
+                // pivot: arg-max of |A[r][k]|, r >= k (lane = row)
+                double best = (lane >= k && lane < ns) ? fabs(A[lane * LD + k]) : -1.0;
+                int p = lane;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int op = __shfl_xor_sync(0xffffffffu, p, o);
+                    if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+                }
+                logdet += log(best);
+                const double ipv = 1.0 / A[p * LD + k];
+                __syncwarp();
+                if (lane < 2 * ns) {                       // lane = column: swap rows k <-> p, scale row k
+                    const double vk = A[k * LD + lane], vp = A[p * LD + lane];
+                    A[p * LD + lane] = vk;
+                    A[k * LD + lane] = vp * ipv;
+                }
+                __syncwarp();
+                if (lane < 2 * ns && lane != k) {          // eliminate column k from every other row
+                    const double akc = A[k * LD + lane];
+                    for (int r = 0; r < ns; ++r)
+                        if (r != k) A[r * LD + lane] = fma(-A[r * LD + k], akc, A[r * LD + lane]);
+                }
+                __syncwarp();
+            }
+            // ---- 3. gradient and Laplacian (lane = particle) -----------------------------------
+            if (deriv) {
+                for (int i = lane; i - lane < ns; i += 32) {
+                    double li = 0.0;
+                    if (i < ns) {
+                        const double* t = Ht + i * kHermStride;
+                        double gx = 0.0, gy = 0.0, cxx = 0.0, cyy = 0.0;
+                        for (int k = 0; k < ns; ++k) {
+                            const int id = orb[i0 + k];
+                            const double* tx = t + 3 * c_orb_nx[id];
+                            const double* ty = t + 24 + 3 * c_orb_ny[id];
+                            const double iv = inv_sqrt_pi * A[k * LD + ns + i];
+                            gx = fma(tx[1] * ty[0], iv, gx);
+                            gy = fma(tx[0] * ty[1], iv, gy);
+                            cxx = fma(tx[2] * ty[0], iv, cxx);
+                            cyy = fma(tx[0] * ty[2], iv, cyy);
+                        }
+                        li = cxx + cyy - gx * gx - gy * gy;
+                        if (a.grad) *reinterpret_cast<double2*>(a.grad + b * D + 2 * (i0 + i)) = make_double2(a.scale * gx, a.scale * gy);
+                    }
+                    lap += li;
+                }
+            }
+            __syncwarp();
+        }
+        if (a.lap) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) lap += __shfl_xor_sync(0xffffffffu, lap, o);
+        }
+        if (lane == 0) {
+            if (a.logabs) a.logabs[b] = a.scale * logdet;
+            if (a.lap) a.lap[b] = a.scale * lap;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Metropolis sampling of |Psi_0|^2 (base_dist.py:58-70, 103-134), one thread per walker.
 // Per-thread matrices live in shared memory, element e of thread t at sm[e * T + t].
 // ---------------------------------------------------------------------------------------

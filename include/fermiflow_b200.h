@@ -62,6 +62,13 @@ int ff_slater_logabsdet(const double* x, long long B, int n, const int* orb, con
 int ff_free_fermion_logp(const double* x, long long B, int n_up, int n_dn, const int* orb,
                          const int* walker_state, double* logp, double* grad, void* stream);
 
+/* The same with the exact Laplacian (sum over all coordinates of d^2 log p0 / dx^2) from Jacobi's
+ * formula -- what utils.py:44-65 y_grad_laplacian returns for f = FreeFermion.log_prob with
+ * 1 + 2N autograd passes (BASELINE.json config "kernel microbench: batched log|det| + exact
+ * Laplacian").  logp, grad, lap nullable. */
+int ff_free_fermion_logp_lap(const double* x, long long B, int n_up, int n_dn, const int* orb,
+                             const int* walker_state, double* logp, double* grad, double* lap, void* stream);
+
 /* FreeFermion.sample / sample_multstates (base_dist.py:58-70, 103-134): Metropolis chain of
  * `steps` whole-configuration moves x' = x + tau N(0,1), started from x ~ N(0,1).
  * Random numbers: Philox4x32-10 keyed by `seed` (counter = walker, step, particle), or,

@@ -208,6 +208,20 @@ def logp_grad_laplacian(x, *model):
     return y.detach(), g.detach().view_as(x), lap
 
 
+def free_fermion_grad_laplacian(orb_up, orb_dn, x):
+    """utils.py:44-65 y_grad_laplacian applied to base_dist.py:48-56 FreeFermion.log_prob:
+    log p0, its gradient and Laplacian through 1 + 2N autograd passes (the reference's path for
+    the BASELINE.json "batched log|det| + exact Laplacian" microbenchmark)."""
+    x = x.detach().clone().requires_grad_(True)
+    xf = x.flatten(1)
+    y = free_fermion_logp(orb_up, orb_dn, xf.view_as(x))
+    g, = torch.autograd.grad(y.sum(), xf, create_graph=True)
+    lap = torch.zeros(x.shape[0])
+    for c in range(xf.shape[1]):
+        lap = lap + torch.autograd.grad(g[:, c].sum(), xf, retain_graph=True)[0][:, c]
+    return y.detach(), g.detach().view_as(x), lap
+
+
 def local_energy(x, orb_up, orb_dn, eta, mu, t_span, nsteps, Z, harmonic=True):
     """VMC.py:46-55: E_loc = -1/4 lap - 1/8 |grad|^2 + V."""
     lp, g, lap = logp_grad_laplacian(x, orb_up, orb_dn, eta, mu, t_span, nsteps)
