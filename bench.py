@@ -203,6 +203,22 @@ def run_ours(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # per-stage breakdown of one step (outside the timed regions; CUDA events on the launch stream)
+    def ev_time(f):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(); r = f(); a1.record(); torch.cuda.synchronize()
+        return a0.elapsed_time(a1), r
+    bd = {}
+    bd["metropolis_ms"], z = ev_time(lambda: model.basedist.sample(model.orbitals_up, model.orbitals_down, (B,)))
+    bd["flow_generate_ms"], x = ev_time(lambda: model.cnf.generate(z))
+    del z, x
+    bd["eloc_sweep_ms"] = eloc_ms
+    t_fwd, gradE = ev_time(lambda: model(B))
+    opt.zero_grad(set_to_none=True)
+    bd["backward_ms"], _ = ev_time(lambda: gradE.backward())
+    bd["forward_total_ms"] = t_fwd
+    del gradE
+
     tms = torch.tensor([ms, e2e_ms], device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -231,7 +247,8 @@ def run_ours(args):
                 "h2d_bytes_per_step": nparam * 8, "d2h_bytes_per_step": (nparam + 2) * 8},
         "gpu_launches": 7 * args.steps,
         "clocks": sampler.summary(),
-        "roofline": {"bound": "fp64", "kernel": "ff::flow_kernel<MODE_ELOC>", "achieved": fl / (eloc_ms * 1e-3) / 1e12,
+        "breakdown_ms": {k: round(v, 2) for k, v in bd.items()},
+        "roofline": {"bound": "fp64", "kernel": "ff::flow_kernel_eloc_static<20,1> (E_loc sweep)", "achieved": fl / (eloc_ms * 1e-3) / 1e12,
                      "peak": peak.value / 1e12, "unit": "TFLOP/s", "frac": fl / (eloc_ms * 1e-3) / peak.value,
                      "peak_source": "ff_fp64_peak DFMA microbenchmark on this device (MEASURED_PEAKS.json has no fp64 entry)",
                      # ncu --set full (profiles/r01_eloc_ncu_full.md): 2.80 GB DRAM traffic for 8288 walkers

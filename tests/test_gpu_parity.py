@@ -444,3 +444,23 @@ def test_eloc_kernel_variants_agree_full_size(dev, B):
             close(getattr(r, k), getattr(res[0], k), 1e-11, 1e-12)
         close(r.stash.y, res[0].stash.y, 1e-13)
         close(r.stash.c, res[0].stash.c, 1e-12, 1e-14)
+
+
+@pytest.mark.parametrize("nup,ndn", [(3, 3), (6, 6), (5, 2), (10, 10), (15, 15)])
+def test_free_fermion_logp_grad_laplacian_vs_oracle(dev, O, nup, ndn):
+    """BASELINE.json config "batched log|det| + exact Laplacian": the fused kernel (one warp per
+    walker) against the reference's way -- 1 + 2N autograd passes through FreeFermion.log_prob
+    (utils.py:44-65) -- and against the CTA-cooperative kernel (FF_SLATER_CTA=1)."""
+    from fermiflow_b200 import HO2D, FreeFermion
+    ho, ff = HO2D(), FreeFermion(dev)
+    n = nup + ndn
+    gen = torch.Generator().manual_seed(100 + n)
+    x = 1.1 * torch.randn(40, n, 2, generator=gen)
+    lp, g, lap = ff.log_prob_grad_laplacian(ho.orbitals[:nup], ho.orbitals[:ndn], x.to(dev))
+    with _env(FF_SLATER_CTA="1"):
+        lp2, g2, lap2 = ff.log_prob_grad_laplacian(ho.orbitals[:nup], ho.orbitals[:ndn], x.to(dev))
+    rlp, rg, rlap = O.free_fermion_grad_laplacian(list(range(nup)), list(range(ndn)), x)
+    # conditioning of the random 15 x 15 Slater matrices limits the agreement at N = 30
+    tol = 1e-10 if n <= 20 else 1e-8
+    close(lp, rlp, tol); close(g, rg, tol); close(lap, rlap, tol)
+    close(lp2, lp, tol); close(g2, g, tol); close(lap2, lap, tol)
