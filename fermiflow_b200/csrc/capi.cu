@@ -197,9 +197,28 @@ int launch_eloc3(ff::FlowArgs& a, cudaStream_t st) {
     return 0;
 }
 
-// Opt-in (FF_ELOC_V3=1): 189 ms against 177 ms of flow_kernel_eloc_static at N = 20, 65536 walkers.
+// Barrier-synchronous sweep with fused phases (ff_eloc2.cuh eloc2_kernel).
+template <int SN, int SMU>
+int launch_eloc2(ff::FlowArgs& a, cudaStream_t st) {
+    constexpr ff::Eloc2Geom g = ff::eloc2_geom(SN, SMU != 0);
+    constexpr ff::Eloc2Launch q = ff::eloc2_launch(SN, SMU != 0);
+    a.D = g.D; a.NP = g.NP; a.P = g.P; a.DP = g.DP; a.NV = g.NV; a.NSV = g.NSV; a.grec = ff::kGRec;
+    a.off_G = g.off_G; a.off_AM = g.off_AM; a.off_u = g.off_u; a.off_kLx = g.off_kLx; a.off_part = g.off_part;
+    a.off_x0 = g.off_x0; a.off_sl = g.off_sl; a.wstride = g.wstride; a.W = 1;
+    const int need = ff::slater_scratch_size(a.n_up, a.n - a.n_up) + 2 * g.D + g.n * g.n + g.NP + 8;
+    if (need > 2 * g.MAT) return fail(-2, "internal: finale scratch does not fit");
+    constexpr int NI = FF_ELOC2_ILP;
+    const int common = ff::kTabDoubles + 6 * (ff::coef_rows2<NI>(a.H_eta) + ff::coef_rows2<NI>(a.H_mu)) + 2 * ((g.NP + 7) / 8) + 2;
+    const size_t smem = (size_t)(common + g.wstride) * 8;
+    if ((long long)smem > dev_info().smem_optin) return 1;
+    return launch_flow_kernel(ff::eloc2_kernel<SN, SMU>, a, q.threads, smem, st);
+}
+
+// Opt-in variants, N = 20, 65536 walkers: FF_ELOC_V3=1 (two-walker pipeline) 183 ms, FF_ELOC_V2=1 (fused phases,
+// barrier-synchronous) 185 ms, against 177 ms of the default flow_kernel_eloc_static.
 int try_eloc_pipeline(ff::FlowArgs& a, cudaStream_t st) {
     if (getenv("FF_ELOC_V3") != nullptr && a.H_mu > 0 && a.n == 20) return launch_eloc3<20, 1>(a, st);
+    if (getenv("FF_ELOC_V2") != nullptr && a.H_mu > 0 && a.n == 20) return launch_eloc2<20, 1>(a, st);
     return 1;
 }
 

@@ -121,4 +121,391 @@ __device__ __forceinline__ double rk_elem(int sub, double s, double hk, double& 
     return fma(hk, 0.125, C);
 }
 
+
+// ---- matrix phases of one RK stage, written for a team of NMT threads (index mt, warps mwarp of MW):
+// the whole CTA in the barrier-synchronous kernel, the matrix warps in the pipeline kernel. ----------
+
+// acc[0] = sum_k acc[k] as a balanced tree (every loop has compile-time bounds: registers only)
+template <int KS>
+__device__ __forceinline__ void tree_sum(double (&acc)[KS][2]) {
+#pragma unroll
+    for (int k = 0; k + 1 < KS; k += 2) { acc[k][0] += acc[k + 1][0]; acc[k][1] += acc[k + 1][1]; }
+#pragma unroll
+    for (int k = 0; k + 2 < KS; k += 4) { acc[k][0] += acc[k + 2][0]; acc[k][1] += acc[k + 2][1]; }
+#pragma unroll
+    for (int k = 0; k + 4 < KS; k += 8) { acc[k][0] += acc[k + 4][0]; acc[k][1] += acc[k + 4][1]; }
+#pragma unroll
+    for (int k = 0; k + 8 < KS; k += 16) { acc[k][0] += acc[k + 8][0]; acc[k][1] += acc[k + 8][1]; }
+#pragma unroll
+    for (int k = 0; k + 16 < KS; k += 32) { acc[k][0] += acc[k + 16][0]; acc[k][1] += acc[k + 16][1]; }
+}
+
+// per-particle sums of the gather records, diagonal 2x2 blocks of A = dv/dy
+template <int SN, int SMU>
+__device__ __forceinline__ void phase_gather(double* S, double* AM, int mt, int NMT) {
+    constexpr Eloc2Geom G_ = eloc2_geom(SN, SMU != 0);
+    constexpr bool has_mu = SMU != 0;
+    constexpr int n = G_.n, D = G_.D, D8 = G_.D8, DP = G_.DP, NP = G_.NP, NB = G_.NB, KS = D8 / 4;
+    (void)n; (void)D; (void)D8; (void)DP; (void)NP; (void)NB; (void)KS;
+    {
+        // sum (i, c) over the n-1 partners of particle i.  Partner slot k < i is pair (k, i)
+        // at record K_k + i (K_k a compile-time constant), slot k >= i is pair (i, k+1) at
+        // record U_i + k + 1: one select + one load + one FMA per term.
+        const double* Gb = S + G_.off_G;
+        for (int q0 = 0; q0 < n * kGRec; q0 += NMT) {
+            const int qr = q0 + mt;
+            const bool active = qr < n * kGRec;
+            const int part = 0;
+            const int q = active ? qr : 0;
+            const int i = q / kGRec, c = q - i * kGRec;
+            const double* pL = Gb + q;                                              // + 11 * (K_k - k - 1)
+            const double* pU = Gb + (i * (2 * n - i - 1) / 2 - i - 1) * kGRec + c;      // + 11 * (k + 1)
+            const double slo = (c < 6) ? -1.0 : 1.0;
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < n - 1; ++k) {
+                const bool lower = k < i;
+                const double* ad = lower ? pL + (k * (2 * n - k - 1) / 2 - k - 1) * kGRec : pU + (k + 1) * kGRec;
+                const double v = *ad, sg = lower ? slo : 1.0;
+                if (k & 1) acc1 = fma(v, sg, acc1); else acc0 = fma(v, sg, acc0);
+            }
+            double acc = acc0 + acc1;
+            if (c == 6 || c == 7) acc *= 0.5;
+            if (has_mu) acc += Gb[(NP + i) * kGRec + c];
+            if (part == 0 && active) {
+                if (c < 2) S[G_.oKy + 2 * i + c] = acc;
+                else if (c < 4) S[G_.off_u + 2 * i + c - 2] = acc;
+                else if (c < 6) S[G_.off_kLx + 2 * i + c - 4] = acc;
+                else if (c < 8) S[G_.off_part + (c - 6) * n + i] = acc;
+                else if (c == 8) AM[(2 * i) * DP + 2 * i] = acc;
+                else if (c == 9) { AM[(2 * i) * DP + 2 * i + 1] = acc; AM[(2 * i + 1) * DP + 2 * i] = acc; }
+                else AM[(2 * i + 1) * DP + 2 * i + 1] = acc;
+            }
+        }
+    }
+}
+
+// J' = A J on the tensor cores (one 8x8 output block per warp task, operands prefetched, independent
+// accumulators per k-step) with the RK4 update of the block in the epilogue: J read from Jc, written to Jn
+template <int SN, int SMU>
+__device__ __forceinline__ void phase_aj_rk(double* S, const double* AM, const double* Jc, double* Jn, int sub, double h,
+                                            int mwarp, int MW, int lane) {
+    constexpr Eloc2Geom G_ = eloc2_geom(SN, SMU != 0);
+    constexpr int n = G_.n, D = G_.D, D8 = G_.D8, DP = G_.DP, NP = G_.NP, NB = G_.NB, KS = D8 / 4;
+    (void)n; (void)D; (void)D8; (void)DP; (void)NP; (void)NB; (void)KS;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    for (int task = mwarp; task < NB * NB; task += MW) {
+        const int rb = task / NB, cb = task - rb * NB;
+        const double* Ap = AM + (8 * rb + g8) * DP + t4;
+        const double* Bp = Jc + t4 * DP + 8 * cb + g8;
+        double av[KS], bv[KS], acc[KS][2];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) { av[k] = Ap[4 * k]; bv[k] = Bp[4 * k * DP]; }
+        const int r = 8 * rb + g8, c = 8 * cb + 2 * t4;
+        const int idx = r * DP + c;
+        const bool inside = r < D && c < D;
+        double2 s = make_double2(0.0, 0.0), Bv = make_double2(0.0, 0.0), Cv = make_double2(0.0, 0.0);
+        if (inside) {
+            s = *reinterpret_cast<const double2*>(Jc + idx);
+            if (sub != 0) {
+                if (sub != 3) Bv = *reinterpret_cast<const double2*>(S + G_.oPB + idx);
+                Cv = *reinterpret_cast<const double2*>(S + G_.oPC + idx);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KS; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; dmma_m8n8k4(acc[k][0], acc[k][1], av[k], bv[k]); }
+        tree_sum<KS>(acc);
+        if (inside) {
+            double2 sn;
+            sn.x = rk_elem(sub, s.x, h * acc[0][0], Bv.x, Cv.x);
+            sn.y = rk_elem(sub, s.y, h * acc[0][1], Bv.y, Cv.y);
+            *reinterpret_cast<double2*>(Jn + idx) = sn;
+            if (sub < 2) *reinterpret_cast<double2*>(S + G_.oPB + idx) = Bv;
+            if (sub < 3) *reinterpret_cast<double2*>(S + G_.oPC + idx) = Cv;
+        }
+    }
+}
+
+// vector part: y' = Ky, L' = A L + kLx, gD' = -(u^T J), Delta' = -rho, lapDelta' = -(sum part2 + u.L);
+// 2 D dot products of length D with four lanes each, RK update by the lane that holds the sum
+template <int SN, int SMU>
+__device__ __forceinline__ void phase_vec_rk(double* S, const double* AM, const double* Jc, const double* Lc, double* Ln,
+                                             int sub, double h, int mt, int NMT, int mwarp, int MW, int lane) {
+    constexpr Eloc2Geom G_ = eloc2_geom(SN, SMU != 0);
+    constexpr int n = G_.n, D = G_.D, D8 = G_.D8, DP = G_.DP, NP = G_.NP, NB = G_.NB, KS = D8 / 4;
+    (void)n; (void)D; (void)D8; (void)DP; (void)NP; (void)NB; (void)KS;
+    {
+        const double* u = S + G_.off_u;
+        constexpr int QD = (D + 3) / 4;                 // terms per lane
+        for (int m0 = 0; m0 < 2 * D; m0 += NMT / 4) {
+            const int mr = m0 + (mt >> 2), part = mt & 3;
+            const bool active = mr < 2 * D;
+            const int m = active ? mr : 0;
+            double acc0 = 0.0, acc1 = 0.0;
+            const int k0 = part * QD;
+            if (m < D) {
+                const double* Ar = AM + m * DP;
+#pragma unroll
+                for (int kk = 0; kk < QD; ++kk) {
+                    const int k = k0 + kk;
+                    if ((D % 4 == 0) || k < D) { if (kk & 1) acc1 = fma(Ar[k], Lc[k], acc1); else acc0 = fma(Ar[k], Lc[k], acc0); }
+                }
+            } else {
+                const double* Jcol = Jc + (m - D);
+#pragma unroll
+                for (int kk = 0; kk < QD; ++kk) {
+                    const int k = k0 + kk;
+                    if ((D % 4 == 0) || k < D) { if (kk & 1) acc1 = fma(u[k], Jcol[k * DP], acc1); else acc0 = fma(u[k], Jcol[k * DP], acc0); }
+                }
+            }
+            double acc = acc0 + acc1;
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (part == 0 && active) {
+                if (m < D) {
+                    const double kL = acc + S[G_.off_kLx + m];
+                    Ln[m] = rk_elem(sub, Lc[m], h * kL, S[G_.oVB + D + m], S[G_.oVC + D + m]);
+                    S[m] = rk_elem(sub, S[m], h * S[G_.oKy + m], S[G_.oVB + m], S[G_.oVC + m]);
+                } else {
+                    const int c = m - D;
+                    S[G_.oGd + c] = rk_elem(sub, S[G_.oGd + c], -h * acc, S[G_.oVB + 2 * D + c], S[G_.oVC + 2 * D + c]);
+                }
+            }
+        }
+        if (mwarp == MW - 1) {
+            const double* part = S + G_.off_part;
+            double rho = 0.0, lp = 0.0;
+            for (int i = lane; i < n; i += 32) { rho += part[i]; lp += part[n + i]; }
+            for (int k = lane; k < D; k += 32) lp = fma(u[k], Lc[k], lp);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                rho += __shfl_xor_sync(0xffffffffu, rho, o);
+                lp += __shfl_xor_sync(0xffffffffu, lp, o);
+            }
+            if (lane < 2) {
+                const double k = lane ? -lp : -rho;
+                S[G_.oS + lane] = rk_elem(sub, S[G_.oS + lane], h * k, S[G_.oVB + 3 * D + lane], S[G_.oVC + 3 * D + lane]);
+            }
+        }
+    }
+}
+
+// M = J J^T (upper block triangle) into AM
+template <int SN, int SMU>
+__device__ __forceinline__ void phase_gram(double* AM, const double* Jn, int mwarp, int MW, int lane) {
+    constexpr Eloc2Geom G_ = eloc2_geom(SN, SMU != 0);
+    constexpr int n = G_.n, D = G_.D, D8 = G_.D8, DP = G_.DP, NP = G_.NP, NB = G_.NB, KS = D8 / 4;
+    (void)n; (void)D; (void)D8; (void)DP; (void)NP; (void)NB; (void)KS;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    for (int blk = mwarp; blk < G_.ntri; blk += MW) {
+        int rb = 0, rem = blk;
+        while (rem >= NB - rb) { rem -= NB - rb; ++rb; }
+        const int cb = rb + rem;
+        const double* Ar = Jn + (8 * rb + g8) * DP + t4;
+        const double* Br = Jn + (8 * cb + g8) * DP + t4;
+        double av[KS], bv[KS], acc[KS][2];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) { av[k] = Ar[4 * k]; bv[k] = Br[4 * k]; }
+#pragma unroll
+        for (int k = 0; k < KS; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; dmma_m8n8k4(acc[k][0], acc[k][1], av[k], bv[k]); }
+        tree_sum<KS>(acc);
+        *reinterpret_cast<double2*>(AM + (8 * rb + g8) * DP + 8 * cb + 2 * t4) = make_double2(acc[0][0], acc[0][1]);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Barrier-synchronous E_loc sweep built from the phases above: one walker per CTA, one thread per
+// item (ceil(P/32) item warps) plus ONE helper warp that computes the Gram matrix while the item
+// warps are in the MLP loop; 256 threads at 128 registers (no spills), two CTAs per SM.
+// Per RK stage: [MLP | Gram] - contractions with M - [A off-diagonal, gather] - [A.J + RK, vectors]:
+// four barriers, no separate derivative block or RK pass.
+// ---------------------------------------------------------------------------------------------
+#ifndef FF_ELOC2_ILP
+#define FF_ELOC2_ILP 5
+#endif
+
+template <int NI>
+__host__ __device__ constexpr int coef_rows2(int H) { return ((H + NI - 1) / NI) * NI; }
+
+struct Eloc2Launch { int item_warps, nwarp, threads; };
+__host__ __device__ constexpr Eloc2Launch eloc2_launch(int n, bool has_mu) {
+    Eloc2Launch q{};
+    const Eloc2Geom g = eloc2_geom(n, has_mu);
+    q.item_warps = (g.P + 31) / 32;
+#ifndef FF_ELOC2_HELPERS
+#define FF_ELOC2_HELPERS 1
+#endif
+    q.nwarp = q.item_warps + FF_ELOC2_HELPERS;
+    if (q.nwarp < 4) q.nwarp = 4;
+    q.threads = 32 * q.nwarp;
+    return q;
+}
+
+template <int SN, int SMU>
+__global__ void __launch_bounds__(eloc2_launch(SN, SMU != 0).threads, (eloc2_launch(SN, SMU != 0).threads <= 320) ? 2 : 1)
+eloc2_kernel(const FlowArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr Eloc2Geom G_ = eloc2_geom(SN, SMU != 0);
+    constexpr Eloc2Launch Q_ = eloc2_launch(SN, SMU != 0);
+    constexpr int n = G_.n, D = G_.D, DP = G_.DP, NP = G_.NP, P = G_.P, MAT = G_.MAT;
+    constexpr int NT = Q_.threads, nwarp = Q_.nwarp, IW = Q_.item_warps, HW = nwarp - IW;
+    constexpr int NI = FF_ELOC2_ILP;
+    constexpr bool has_mu = SMU != 0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    double* tab = smem;
+    double* coef_eta = tab + kTabDoubles;
+    double* coef_mu = coef_eta + 6 * coef_rows2<NI>(a.H_eta);
+    const int cbase = kTabDoubles + 6 * (coef_rows2<NI>(a.H_eta) + coef_rows2<NI>(a.H_mu));
+    unsigned char* pair_i = reinterpret_cast<unsigned char*>(smem + cbase);
+    unsigned char* pair_j = pair_i + ((NP + 7) & ~7);
+    double* S = smem + cbase + 2 * ((NP + 7) / 8);
+    if ((S - smem) & 1) S += 1;
+
+    fill_exp_table(tab);
+    const double* tabl = tab + (tid & 15);
+    for (int r = tid; r < coef_rows2<NI>(a.H_eta) + (has_mu ? coef_rows2<NI>(a.H_mu) : 0); r += NT) {
+        const bool e = r < coef_rows2<NI>(a.H_eta);
+        const int hh = e ? r : r - coef_rows2<NI>(a.H_eta), H = e ? a.H_eta : a.H_mu;
+        double w = 0.0, b = 0.0, c = 0.0;
+        if (hh < H) { w = (e ? a.eta_w1 : a.mu_w1)[hh]; b = (e ? a.eta_b1 : a.mu_b1)[hh]; c = (e ? a.eta_w2 : a.mu_w2)[hh]; }
+        double* o = (e ? coef_eta : coef_mu) + 6 * hh;
+        o[0] = w; o[1] = b; o[2] = c; o[3] = c * w; o[4] = c * w * w; o[5] = c * w * w * w;
+    }
+    for (int p = tid; p < NP; p += NT) {
+        int i = 0, rem = p;
+        while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+        pair_i[p] = (unsigned char)i;
+        pair_j[p] = (unsigned char)(i + 1 + rem);
+    }
+    for (int e = tid; e < MAT; e += NT) { S[G_.oJ1 + e] = 0.0; S[G_.off_AM + e] = 0.0; }   // zero padding, once
+    __syncthreads();
+
+    const double h = (a.tb - a.ta) / a.nsteps;
+    const int NS = 4 * a.nsteps;
+    const bool it_valid = tid < P;
+    const int it_p = it_valid ? tid : 0;
+    const bool it_pair = it_p < NP;
+    const int it_i = it_pair ? pair_i[it_p] : it_p - NP;
+    const int it_j = it_pair ? pair_j[it_p] : it_i;
+    double* const Grec = S + G_.off_G + it_p * kGRec;
+    double* const AM = S + G_.off_AM;
+
+#ifdef FF_PHASE_TIMING
+    __shared__ long long tsh[16];
+    const bool OBS = tid == (FF_PHASE_TIMING) * 32;
+    if (OBS) { for (int k = 0; k < 15; ++k) tsh[k] = 0; tsh[15] = clock64(); }
+#endif
+    for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+        for (int e = tid; e < G_.NSV; e += NT) {
+            double v = 0.0;
+            if (e < D) { v = a.x_in[b * D + e]; S[G_.off_x0 + e] = v; }
+            else if (e >= G_.oJ0) {
+                const int r = (e - G_.oJ0) / DP, c = (e - G_.oJ0) - r * DP;
+                v = (r == c && r < D) ? 1.0 : 0.0;
+            }
+            S[e] = v;
+        }
+        __syncthreads();
+        for (int stage = 0; stage < NS; ++stage) {
+            FF_TICK2(0);
+            const int sub = stage & 3, cur = stage & 1;
+            const double* Jc = S + (cur ? G_.oJ1 : G_.oJ0);
+            double* Jn = S + (cur ? G_.oJ0 : G_.oJ1);
+            const double* Lc = S + (cur ? G_.oL1 : G_.oL);
+            double* Ln = S + (cur ? G_.oL : G_.oL1);
+            // ======== phase A: radial MLPs on the item warps, Gram matrix on the helper ==========
+            double rx = 0, ry = 0, ca = 0, cb_ = 0, ccq = 0, ceq = 0, cf = 0;
+            if (warp < IW) {
+                const double* y = S;
+                if (it_pair) { rx = y[2 * it_i] - y[2 * it_j]; ry = y[2 * it_i + 1] - y[2 * it_j + 1]; }
+                else { rx = y[2 * it_i]; ry = y[2 * it_i + 1]; }
+                const double d2 = fma(rx, rx, ry * ry);
+                const double inv_d = rsqrt(d2);
+                const double d = d2 * inv_d;
+                double f[4];
+                FF_TICK2(1);
+                radial_mlp_n<3, NI>(it_pair ? coef_eta : coef_mu, it_pair ? a.H_eta : a.H_mu, d, tabl, f);
+                FF_TICK2(2);
+                if (it_valid) {
+                    if (a.stash_c != nullptr) {
+                        double* sc = a.stash_c + ((b * NS + stage) * P + it_p) * 3;
+                        sc[0] = f[0]; sc[1] = f[1]; sc[2] = f[2];
+                    }
+                    const double mult = it_pair ? 2.0 : 1.0;
+                    const double inv_d2 = inv_d * inv_d;
+                    cf = f[0];
+                    ca = f[1] * inv_d;
+                    cb_ = (f[2] - ca) * inv_d2;
+                    const double q1 = mult * fma(f[2], d, 3.0 * f[1]);
+                    const double q2 = mult * fma(f[3], d, 4.0 * f[2]);
+                    ccq = q1 * inv_d;
+                    ceq = (q2 - ccq) * inv_d2;
+                    Grec[0] = cf * rx; Grec[1] = cf * ry;
+                    Grec[2] = ccq * rx; Grec[3] = ccq * ry;
+                    Grec[6] = mult * fma(f[1], d, 2.0 * f[0]);
+                    Grec[8] = fma(ca * rx, rx, cf);
+                    Grec[9] = ca * rx * ry;
+                    Grec[10] = fma(ca * ry, ry, cf);
+                }
+            } else {
+                if (a.stash_y != nullptr)
+                    for (int e = tid - 32 * IW; e < D; e += 32 * HW) a.stash_y[(b * NS + stage) * D + e] = S[e];
+                phase_gram<SN, SMU>(AM, Jc, warp - IW, HW, lane);
+            }
+            FF_TICK2(3);
+            __syncthreads();
+            FF_TICK2(4);
+            // ======== phase B: contractions with M = J J^T ======================================
+            if (it_valid) {
+                const double* M = AM;
+                const int i2 = 2 * it_i, j2 = 2 * it_j;
+                double w00, w01, w11;
+                if (it_pair) {
+                    w00 = M[i2 * DP + i2] + M[j2 * DP + j2] - 2.0 * M[i2 * DP + j2];
+                    w11 = M[(i2 + 1) * DP + i2 + 1] + M[(j2 + 1) * DP + j2 + 1] - 2.0 * M[(i2 + 1) * DP + j2 + 1];
+                    w01 = M[i2 * DP + i2 + 1] + M[j2 * DP + j2 + 1] - M[i2 * DP + j2 + 1] - M[(i2 + 1) * DP + j2];
+                } else {
+                    w00 = M[i2 * DP + i2]; w01 = M[i2 * DP + i2 + 1]; w11 = M[(i2 + 1) * DP + i2 + 1];
+                }
+                const double wrx = fma(w00, rx, w01 * ry), wry = fma(w01, rx, w11 * ry);
+                const double trw = w00 + w11, rwr = fma(rx, wrx, ry * wry);
+                Grec[4] = fma(ca, fma(2.0, wrx, trw * rx), cb_ * rwr * rx);
+                Grec[5] = fma(ca, fma(2.0, wry, trw * ry), cb_ * rwr * ry);
+                Grec[7] = fma(ccq, trw, ceq * rwr);
+            }
+            FF_TICK2(5);
+            __syncthreads();
+            FF_TICK2(6);
+            // ======== phase C: A = dv/dy (off-diagonal blocks by the items), per-particle sums ==
+            if (it_valid && it_pair) {
+                const double a00 = -fma(ca * rx, rx, cf), a01 = -(ca * rx * ry), a11 = -fma(ca * ry, ry, cf);
+                const int i2 = 2 * it_i, j2 = 2 * it_j;
+                *reinterpret_cast<double2*>(AM + i2 * DP + j2) = make_double2(a00, a01);
+                *reinterpret_cast<double2*>(AM + (i2 + 1) * DP + j2) = make_double2(a01, a11);
+                *reinterpret_cast<double2*>(AM + j2 * DP + i2) = make_double2(a00, a01);
+                *reinterpret_cast<double2*>(AM + (j2 + 1) * DP + i2) = make_double2(a01, a11);
+            }
+            phase_gather<SN, SMU>(S, AM, tid, NT);
+            FF_TICK2(7);
+            __syncthreads();
+            FF_TICK2(8);
+            // ======== phase D: stage derivative with the RK update fused in ======================
+            phase_aj_rk<SN, SMU>(S, AM, Jc, Jn, sub, h, warp, nwarp, lane);
+            FF_TICK2(9);
+            phase_vec_rk<SN, SMU>(S, AM, Jc, Lc, Ln, sub, h, tid, NT, warp, nwarp, lane);
+            FF_TICK2(10);
+            __syncthreads();
+            FF_TICK2(11);
+        }
+#ifdef FF_PHASE_TIMING
+        if (OBS) { for (int k = 0; k < 15; ++k) { atomicAdd(&g_phase_cycles[k], (unsigned long long)tsh[k]); tsh[k] = 0; } }
+#endif
+        if (a.y_out) for (int e = tid; e < D; e += NT) a.y_out[b * D + e] = S[e];
+        if (a.delta_out && tid == 0) a.delta_out[b] = S[G_.oS];
+        eloc_finale(a, b, S, pair_i, pair_j);
+    }
+}
+
 }  // namespace ff

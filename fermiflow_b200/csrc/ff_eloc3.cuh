@@ -70,21 +70,6 @@ __device__ __forceinline__ void load_mlp_coef_halves(double* coef, const double*
     }
 }
 
-// acc[0] = sum_k acc[k] as a balanced tree (every loop has compile-time bounds: registers only)
-template <int KS>
-__device__ __forceinline__ void tree_sum(double (&acc)[KS][2]) {
-#pragma unroll
-    for (int k = 0; k + 1 < KS; k += 2) { acc[k][0] += acc[k + 1][0]; acc[k][1] += acc[k + 1][1]; }
-#pragma unroll
-    for (int k = 0; k + 2 < KS; k += 4) { acc[k][0] += acc[k + 2][0]; acc[k][1] += acc[k + 2][1]; }
-#pragma unroll
-    for (int k = 0; k + 4 < KS; k += 8) { acc[k][0] += acc[k + 4][0]; acc[k][1] += acc[k + 4][1]; }
-#pragma unroll
-    for (int k = 0; k + 8 < KS; k += 16) { acc[k][0] += acc[k + 8][0]; acc[k][1] += acc[k + 8][1]; }
-#pragma unroll
-    for (int k = 0; k + 16 < KS; k += 32) { acc[k][0] += acc[k + 16][0]; acc[k][1] += acc[k + 16][1]; }
-}
-
 #ifndef FF_ELOC3_ILP
 #define FF_ELOC3_ILP 5
 #endif
@@ -291,133 +276,16 @@ eloc3_kernel(const FlowArgs a) {
             double* AM = S + G_.off_AM;
             // ---- per-particle sums, diagonal blocks of A -------------------------------------
 #ifndef FF_EXP_NO_MATRIX
-            {
-                // sum (i, c) over the n-1 partners of particle i.  Partner slot k < i is pair (k, i)
-                // at record K_k + i (K_k a compile-time constant), slot k >= i is pair (i, k+1) at
-                // record U_i + k + 1: one select + one load + one FMA per term.
-                const double* Gb = S + G_.off_G;
-                for (int q0 = 0; q0 < n * kGRec; q0 += NMT) {
-                    const int qr = q0 + mt;
-                    const bool active = qr < n * kGRec;
-                    const int part = 0;
-                    const int q = active ? qr : 0;
-                    const int i = q / kGRec, c = q - i * kGRec;
-                    const double* pL = Gb + q;                                              // + 11 * (K_k - k - 1)
-                    const double* pU = Gb + (i * (2 * n - i - 1) / 2 - i - 1) * kGRec + c;      // + 11 * (k + 1)
-                    const double slo = (c < 6) ? -1.0 : 1.0;
-                    double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-                    for (int k = 0; k < n - 1; ++k) {
-                        const bool lower = k < i;
-                        const double* ad = lower ? pL + (k * (2 * n - k - 1) / 2 - k - 1) * kGRec : pU + (k + 1) * kGRec;
-                        const double v = *ad, sg = lower ? slo : 1.0;
-                        if (k & 1) acc1 = fma(v, sg, acc1); else acc0 = fma(v, sg, acc0);
-                    }
-                    double acc = acc0 + acc1;
-                    if (c == 6 || c == 7) acc *= 0.5;
-                    if (has_mu) acc += Gb[(NP + i) * kGRec + c];
-                    if (part == 0 && active) {
-                        if (c < 2) S[G_.oKy + 2 * i + c] = acc;
-                        else if (c < 4) S[G_.off_u + 2 * i + c - 2] = acc;
-                        else if (c < 6) S[G_.off_kLx + 2 * i + c - 4] = acc;
-                        else if (c < 8) S[G_.off_part + (c - 6) * n + i] = acc;
-                        else if (c == 8) AM[(2 * i) * DP + 2 * i] = acc;
-                        else if (c == 9) { AM[(2 * i) * DP + 2 * i + 1] = acc; AM[(2 * i + 1) * DP + 2 * i] = acc; }
-                        else AM[(2 * i + 1) * DP + 2 * i + 1] = acc;
-                    }
-                }
-            }
+            phase_gather<SN, SMU>(S, AM, mt, NMT);
             FF_TICK2(5);
             team.sync();
             FF_TICK2(6);
             // ---- J' = A J with the RK update in the epilogue -----------------------------------
-            for (int task = mwarp; task < NB * NB; task += MW) {
-                const int rb = task / NB, cb = task - rb * NB;
-                const double* Ap = AM + (8 * rb + g8) * DP + t4;
-                const double* Bp = Jc + t4 * DP + 8 * cb + g8;
-                double av[KS], bv[KS], acc[KS][2];
-#pragma unroll
-                for (int k = 0; k < KS; ++k) { av[k] = Ap[4 * k]; bv[k] = Bp[4 * k * DP]; }
-                const int r = 8 * rb + g8, c = 8 * cb + 2 * t4;
-                const int idx = r * DP + c;
-                const bool inside = r < D && c < D;
-                double2 s = make_double2(0.0, 0.0), Bv = make_double2(0.0, 0.0), Cv = make_double2(0.0, 0.0);
-                if (inside) {
-                    s = *reinterpret_cast<const double2*>(Jc + idx);
-                    if (sub != 0) {
-                        if (sub != 3) Bv = *reinterpret_cast<const double2*>(S + G_.oPB + idx);
-                        Cv = *reinterpret_cast<const double2*>(S + G_.oPC + idx);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < KS; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; dmma_m8n8k4(acc[k][0], acc[k][1], av[k], bv[k]); }
-                tree_sum<KS>(acc);
-                if (inside) {
-                    double2 sn;
-                    sn.x = rk_elem(sub, s.x, h * acc[0][0], Bv.x, Cv.x);
-                    sn.y = rk_elem(sub, s.y, h * acc[0][1], Bv.y, Cv.y);
-                    *reinterpret_cast<double2*>(Jn + idx) = sn;
-                    if (sub < 2) *reinterpret_cast<double2*>(S + G_.oPB + idx) = Bv;
-                    if (sub < 3) *reinterpret_cast<double2*>(S + G_.oPC + idx) = Cv;
-                }
-            }
+            phase_aj_rk<SN, SMU>(S, AM, Jc, Jn, sub, h, mwarp, MW, lane);
             FF_TICK2(7);
             // ---- vector part: 2 D dot products of length D, four lanes each ---------------------
             //   y' = Ky,  L' = A L + kLx,  gD' = -(u^T J),  Delta' = -rho,  lapDelta' = -(sum part2 + u.L)
-            {
-                const double* u = S + G_.off_u;
-                constexpr int QD = (D + 3) / 4;                 // terms per lane
-                for (int m0 = 0; m0 < 2 * D; m0 += NMT / 4) {
-                    const int mr = m0 + (mt >> 2), part = mt & 3;
-                    const bool active = mr < 2 * D;
-                    const int m = active ? mr : 0;
-                    double acc0 = 0.0, acc1 = 0.0;
-                    const int k0 = part * QD;
-                    if (m < D) {
-                        const double* Ar = AM + m * DP;
-#pragma unroll
-                        for (int kk = 0; kk < QD; ++kk) {
-                            const int k = k0 + kk;
-                            if ((D % 4 == 0) || k < D) { if (kk & 1) acc1 = fma(Ar[k], Lc[k], acc1); else acc0 = fma(Ar[k], Lc[k], acc0); }
-                        }
-                    } else {
-                        const double* Jcol = Jc + (m - D);
-#pragma unroll
-                        for (int kk = 0; kk < QD; ++kk) {
-                            const int k = k0 + kk;
-                            if ((D % 4 == 0) || k < D) { if (kk & 1) acc1 = fma(u[k], Jcol[k * DP], acc1); else acc0 = fma(u[k], Jcol[k * DP], acc0); }
-                        }
-                    }
-                    double acc = acc0 + acc1;
-                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                    if (part == 0 && active) {
-                        if (m < D) {
-                            const double kL = acc + S[G_.off_kLx + m];
-                            Ln[m] = rk_elem(sub, Lc[m], h * kL, S[G_.oVB + D + m], S[G_.oVC + D + m]);
-                            S[m] = rk_elem(sub, S[m], h * S[G_.oKy + m], S[G_.oVB + m], S[G_.oVC + m]);
-                        } else {
-                            const int c = m - D;
-                            S[G_.oGd + c] = rk_elem(sub, S[G_.oGd + c], -h * acc, S[G_.oVB + 2 * D + c], S[G_.oVC + 2 * D + c]);
-                        }
-                    }
-                }
-                if (mwarp == MW - 1) {
-                    const double* part = S + G_.off_part;
-                    double rho = 0.0, lp = 0.0;
-                    for (int i = lane; i < n; i += 32) { rho += part[i]; lp += part[n + i]; }
-                    for (int k = lane; k < D; k += 32) lp = fma(u[k], Lc[k], lp);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        rho += __shfl_xor_sync(0xffffffffu, rho, o);
-                        lp += __shfl_xor_sync(0xffffffffu, lp, o);
-                    }
-                    if (lane < 2) {
-                        const double k = lane ? -lp : -rho;
-                        S[G_.oS + lane] = rk_elem(sub, S[G_.oS + lane], h * k, S[G_.oVB + 3 * D + lane], S[G_.oVC + 3 * D + lane]);
-                    }
-                }
-            }
+            phase_vec_rk<SN, SMU>(S, AM, Jc, Lc, Ln, sub, h, mt, NMT, mwarp, MW, lane);
 #endif  // FF_EXP_NO_MATRIX
             FF_TICK2(8);
             team.sync();
@@ -427,20 +295,7 @@ eloc3_kernel(const FlowArgs a) {
 #else
             if (stage + 1 < NS) {
                 // ---- M = J J^T of the new state, for the item threads' next turn --------------
-                for (int blk = mwarp; blk < G_.ntri; blk += MW) {
-                    int rb = 0, rem = blk;
-                    while (rem >= NB - rb) { rem -= NB - rb; ++rb; }
-                    const int cb = rb + rem;
-                    const double* Ar = Jn + (8 * rb + g8) * DP + t4;
-                    const double* Br = Jn + (8 * cb + g8) * DP + t4;
-                    double av[KS], bv[KS], acc[KS][2];
-#pragma unroll
-                    for (int k = 0; k < KS; ++k) { av[k] = Ar[4 * k]; bv[k] = Br[4 * k]; }
-#pragma unroll
-                    for (int k = 0; k < KS; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; dmma_m8n8k4(acc[k][0], acc[k][1], av[k], bv[k]); }
-                    tree_sum<KS>(acc);
-                    *reinterpret_cast<double2*>(AM + (8 * rb + g8) * DP + 8 * cb + 2 * t4) = make_double2(acc[0][0], acc[0][1]);
-                }
+                phase_gram<SN, SMU>(AM, Jn, mwarp, MW, lane);
                 if (slot) sg1 = stage + 1; else sg0 = stage + 1;
             } else
 #endif

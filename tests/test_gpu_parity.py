@@ -430,13 +430,14 @@ def test_flow_kernel_variants_agree_full_size(dev):
 @pytest.mark.parametrize("B", [1, 2, 297, 1500])
 def test_eloc_kernel_variants_agree_full_size(dev, B):
     """N = 20: the statically specialised sweep (default), the generic flow_kernel<MODE_ELOC>
-    (FF_NO_STATIC=1, the one pinned against the oracle at small N) and the warp-specialised
-    two-walker pipeline (FF_ELOC_V3=1; odd walker counts exercise its slot shutdown)."""
+    (FF_NO_STATIC=1, the one pinned against the oracle at small N), the warp-specialised
+    two-walker pipeline (FF_ELOC_V3=1; odd walker counts exercise its slot shutdown) and the
+    barrier-synchronous kernel with fused phases (FF_ELOC_V2=1)."""
     model = _n20_model(dev, nsteps=4)
     _, x = model.sample((B,))
     res = []
-    for env in (dict(FF_NO_STATIC=None, FF_ELOC_V3=None), dict(FF_NO_STATIC="1", FF_ELOC_V3=None),
-                dict(FF_NO_STATIC=None, FF_ELOC_V3="1")):
+    for env in (dict(FF_NO_STATIC=None, FF_ELOC_V3=None, FF_ELOC_V2=None), dict(FF_NO_STATIC="1", FF_ELOC_V3=None, FF_ELOC_V2=None),
+                dict(FF_NO_STATIC=None, FF_ELOC_V3="1", FF_ELOC_V2=None), dict(FF_NO_STATIC=None, FF_ELOC_V3=None, FF_ELOC_V2="1")):
         with _env(**env):
             res.append(model.local_energy(x, stash=True))
     for r in res[1:]:
