@@ -417,6 +417,144 @@ __global__ void __launch_bounds__(128) metropolis_kernel(const MetroArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Metropolis sampling with ONE WARP PER WALKER (spin blocks of at most 16 particles).
+// Same chain as metropolis_kernel -- same Philox counters, same proposal, the same LU arithmetic
+// element by element, hence bit-identical samples -- but the n Box-Muller pairs of a move are drawn
+// by n lanes at once, the 1D oscillator values come from a per-particle table and the two spin
+// blocks are factorised side by side: lanes 0-15 own the columns of Phi_up, lanes 16-31 those of
+// Phi_down, pivots are found with 16-wide shuffles.
+// ---------------------------------------------------------------------------------------
+constexpr int kMetroHerm = 17;       // doubles per particle in the value table (2 x 8, odd stride)
+__host__ __device__ inline int metro_warp_slice(int n, int nmax) {
+    return ff_even(2 * 2 * n + n * kMetroHerm + 2 * nmax * (nmax + 1) + 2);
+}
+
+__global__ void __launch_bounds__(256) metropolis_warp_kernel(const MetroArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int n = a.n, D = 2 * n, n_up = a.n_up, n_dn = n - n_up;
+    const int nmax = max(n_up, n_dn), LD = nmax + 1;
+    double* X = smem + (size_t)warp * metro_warp_slice(n, nmax);
+    double* Y = X + D;
+    double* Ht = Y + D;                       // [n][kMetroHerm]
+    double* A0 = Ht + n * kMetroHerm;         // two blocks of nmax x LD
+    const double inv_sqrt_pi = 0.56418958354775628695;
+    const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    const int half = lane >> 4, hl = lane & 15;            // spin block / column of this lane
+    const int ns = half ? n_dn : n_up, i0 = half ? n_up : 0;
+    double* A = A0 + half * nmax * LD;
+    const long long wstride = (long long)gridDim.x * nwarp;
+
+    for (long long b = (long long)blockIdx.x * nwarp + warp; b < a.B; b += wstride) {
+        const int* orb = a.orb + (size_t)(a.walker_state ? a.walker_state[b] : 0) * n;
+        const unsigned long long wid = (unsigned long long)(b + a.walker_offset);
+        auto normal_pair = [&](uint32_t step, uint32_t slot, double& g0, double& g1) {
+            uint4 r = philox4x32_10(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), step, slot), key);
+            const double u1 = u01_53(r.x, r.y), u2 = u01_53(r.z, r.w);
+            const double rad = sqrt(-2.0 * log(u1));
+            double sn, cs;
+            sincospi(2.0 * u2, &sn, &cs);
+            g0 = rad * cs; g1 = rad * sn;
+        };
+        // log|Psi_0|^2 of the configuration in Z (both spin blocks at once)
+        auto logprob = [&](const double* Z) -> double {
+            for (int e = lane; e < D; e += 32) {                       // 1D oscillator values
+                double v[8];
+                hermite_values(Z[e], v);
+                double* t = Ht + (e >> 1) * kMetroHerm + (e & 1) * 8;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) t[q] = v[q];
+            }
+            __syncwarp();
+            if (hl < ns) {                                             // lane = (block, column c): Phi[r][c]
+                const int id = orb[i0 + hl];
+                const int nx = c_orb_nx[id], ny = c_orb_ny[id];
+                for (int r = 0; r < ns; ++r) {
+                    const double* t = Ht + (i0 + r) * kMetroHerm;
+                    A[r * LD + hl] = inv_sqrt_pi * t[nx] * t[8 + ny];
+                }
+            }
+            __syncwarp();
+            double ld = 0.0;
+            for (int k = 0; k < nmax; ++k) {
+                const bool on = k < ns;                                // this half still has pivots to do
+                // pivot: first maximum of |A[r][k]|, r >= k, lane hl = row
+                double best = (on && hl >= k && hl < ns) ? fabs(A[hl * LD + k]) : -1.0;
+                int p = hl;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, o, 16);
+                    const int op = __shfl_xor_sync(0xffffffffu, p, o, 16);
+                    if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+                }
+                __syncwarp();
+                if (on) {
+                    if (p != k && hl >= k && hl < ns) {                // swap rows k <-> p, columns c >= k
+                        const double t = A[k * LD + hl];
+                        A[k * LD + hl] = A[p * LD + hl];
+                        A[p * LD + hl] = t;
+                    }
+                    ld += log(best);
+                }
+                __syncwarp();
+                if (on && hl > k && hl < ns) {                         // eliminate below the pivot, columns c > k
+                    const double ipv = 1.0 / A[k * LD + k];
+                    const double akc = A[k * LD + hl];
+                    for (int r = k + 1; r < ns; ++r) {
+                        const double l = A[r * LD + k] * ipv;
+                        A[r * LD + hl] = fma(-l, akc, A[r * LD + hl]);
+                    }
+                }
+                __syncwarp();
+            }
+            const double lu = __shfl_sync(0xffffffffu, ld, 0), ldn = __shfl_sync(0xffffffffu, ld, 16);
+            return 2.0 * ((n_up ? lu : 0.0) + (n_dn ? ldn : 0.0));
+        };
+
+        for (int i = lane; i < n; i += 32) {
+            double g0, g1;
+            if (a.x0) { g0 = a.x0[b * D + 2 * i]; g1 = a.x0[b * D + 2 * i + 1]; }
+            else normal_pair(0u, (uint32_t)i, g0, g1);
+            X[2 * i] = g0; X[2 * i + 1] = g1;
+        }
+        __syncwarp();
+        double logp = logprob(X);
+        int acc = 0;
+        for (int s = 0; s < a.steps; ++s) {
+            for (int i = lane; i < n; i += 32) {
+                double g0, g1;
+                if (a.normals) {
+                    const double* e = a.normals + ((size_t)s * a.B + b) * D + 2 * i;
+                    g0 = e[0]; g1 = e[1];
+                } else normal_pair((uint32_t)(s + 1), (uint32_t)i, g0, g1);
+                Y[2 * i] = fma(a.tau, g0, X[2 * i]);
+                Y[2 * i + 1] = fma(a.tau, g1, X[2 * i + 1]);
+            }
+            __syncwarp();
+            const double nlogp = logprob(Y);
+            double u = 0.0;
+            if (lane == 0) {
+                if (a.uniforms) u = a.uniforms[(size_t)s * a.B + b];
+                else {
+                    uint4 r = philox4x32_10(make_uint4((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)(s + 1), 0xFFFFFFFFu), key);
+                    u = u01_53(r.x, r.y);
+                }
+            }
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u < exp(nlogp - logp)) {                               // warp-uniform decision
+                for (int e = lane; e < D; e += 32) X[e] = Y[e];
+                logp = nlogp;
+                ++acc;
+            }
+            __syncwarp();
+        }
+        for (int e = lane; e < D; e += 32) a.x[b * D + e] = X[e];
+        if (a.accept_count && lane == 0) a.accept_count[b] = acc;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // potentials.py: 1/2 sum r^2 and Z sum_{i<j} 1/r_ij, one thread per walker.
 // ---------------------------------------------------------------------------------------
 __global__ void potential_kernel(const double* x, long long B, int n, double Z, int harmonic, double* V) {

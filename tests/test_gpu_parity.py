@@ -465,3 +465,19 @@ def test_free_fermion_logp_grad_laplacian_vs_oracle(dev, O, nup, ndn):
     tol = 1e-10 if n <= 20 else 1e-8
     close(lp, rlp, tol); close(g, rg, tol); close(lap, rlap, tol)
     close(lp2, lp, tol); close(g2, g, tol); close(lap2, lap, tol)
+
+
+@pytest.mark.parametrize("nup,ndn", [(10, 10), (3, 0), (6, 5)])
+def test_metropolis_kernels_bit_identical(dev, nup, ndn):
+    """The one-warp-per-walker sampler reproduces the one-thread-per-walker chain bit for bit
+    (same Philox counters, same LU arithmetic), including the acceptance counts."""
+    from fermiflow_b200 import HO2D, FreeFermion
+    ho = HO2D()
+    outs = []
+    for env in (dict(FF_METRO_THREAD=None), dict(FF_METRO_THREAD="1")):
+        with _env(**env):
+            ff = FreeFermion(dev)
+            ff.manual_seed(77)
+            outs.append(ff.sample(ho.orbitals[:nup], ho.orbitals[:ndn], (1000,), equilibrim_steps=40))
+    assert torch.equal(outs[0], outs[1])
+    assert torch.isfinite(outs[0]).all()
