@@ -63,3 +63,19 @@ def test_energy_statistically_consistent_with_reference_algorithm(dev):
     E, E_std, _ = R.vmc_iteration(2, 2, params, True, 2.0, 96)
     se_ref = E_std / math.sqrt(96)
     assert abs(e_gpu - E) < 4.0 * math.hypot(se_gpu, se_ref), (e_gpu, se_gpu, E, se_ref)
+
+
+def test_strong_coupling_finite_temperature_run(dev):
+    """BASELINE config 3 (short): Wigner-molecule regime Z = 8, N = 12 spin-polarised fermions, finer
+    ODE grid (32 RK4 steps), finite temperature with the Boltzmann occupation sampler."""
+    from fermiflow_b200 import BetaFermionHO2D
+    torch.manual_seed(0)
+    hist = BetaFermionHO2D.main(["--beta", "2.0", "--nup", "12", "--Z", "8.0", "--deltaE", "2.0", "--boltzmann",
+                                 "--batch", "2048", "--iternum", "12", "--nsteps", "32", "--Deta", "16", "--Dmu", "16",
+                                 "--lr", "2e-2"])
+    F = [h[0] for h in hist]
+    assert all(math.isfinite(v) for h in hist for v in h)
+    # the free energy of the trial state drops quickly from the non-interacting starting point
+    assert sum(F[-3:]) / 3 < sum(F[:3]) / 3 - 0.5, F
+    # entropy stays within the bounds of the sampled state space
+    assert all(-1e-9 <= h[4] for h in hist)
