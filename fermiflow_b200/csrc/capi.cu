@@ -66,6 +66,44 @@ int check_model(const ff_model* m) {
 
 inline int even(int x) { return (x + 1) & ~1; }
 
+// Certified Taylor tables of the radial functions for one sweep launch (ff_radial_table.cuh): built from
+// the current parameters on the launch stream, released stream-ordered after the sweep.
+// FF_NO_TABLE=1 keeps the direct evaluation of every hidden unit.
+struct RadialTables {
+    double* buf = nullptr;
+    cudaStream_t st = nullptr;
+    int build(const ff_model* m, cudaStream_t stream, ff::FlowArgs& a) {
+        a.rt_eta = nullptr; a.rt_mu = nullptr;
+        if (getenv("FF_NO_TABLE") != nullptr) return 0;
+        st = stream;
+        {   // keep the stream-ordered pool's memory across synchronisation points (default: trimmed at every sync)
+            static thread_local bool pool_ready[16] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (!pool_ready[dev & 15]) {
+                cudaMemPool_t pool;
+                if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                    unsigned long long keep = 64ull << 20;
+                    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                }
+                pool_ready[dev & 15] = true;
+            }
+        }
+        const size_t per = ff::radial_table_doubles();
+        FF_CUDA(cudaMallocAsync((void**)&buf, 2 * per * sizeof(double), st));
+        ff::RadialBuildArgs b{};
+        b.w1[0] = m->eta_w1; b.b1[0] = m->eta_b1; b.w2[0] = m->eta_w2; b.H[0] = m->H_eta; b.table[0] = buf;
+        b.w1[1] = m->mu_w1; b.b1[1] = m->mu_b1; b.w2[1] = m->mu_w2; b.H[1] = m->H_mu; b.table[1] = m->H_mu > 0 ? buf + per : nullptr;
+        ff::radial_table_build_kernel<<<dim3(ff::kRtMaxNodes / 128, 2), 128, 0, st>>>(b);
+        FF_CUDA(cudaGetLastError());
+        ff::radial_table_check_kernel<<<dim3(1, 2), 128, 0, st>>>(b.table[0], b.table[1]);
+        FF_CUDA(cudaGetLastError());
+        a.rt_eta = b.table[0]; a.rt_mu = b.table[1];
+        return 0;
+    }
+    ~RadialTables() { if (buf) cudaFreeAsync(buf, st); }
+};
+
 // Fills the geometry fields of FlowArgs and returns threads / dynamic smem bytes.
 int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t& smem) {
     const DevInfo di = dev_info();
@@ -106,7 +144,9 @@ int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t
     a.W = W;
     threads = ((W * a.P + 31) / 32) * 32;
     if (threads < 64) threads = 64;
-    if (eloc && threads + 32 <= 256) threads += 32;      // helper warp: Gram matrix overlaps the MLP loop
+    // helper warp: its Gram matrix overlaps the MLP loop of the item warps (direct evaluation only; with the
+    // Taylor tables the item phase is short and every warp shares the Gram matrix)
+    if (eloc && threads + 32 <= 256 && getenv("FF_NO_TABLE") != nullptr) threads += 32;
     smem = (size_t)(common + (long long)W * a.wstride) * 8;
     return 0;
 }
@@ -163,7 +203,11 @@ int launch_flow(ff::FlowArgs& a, int threads, size_t smem, cudaStream_t st) {
     }
     if (MODE == ff::MODE_ELOC && a.W == 1 && a.H_mu > 0 && getenv("FF_NO_STATIC") == nullptr) {
         // statically specialised sweeps for the benchmark sizes (BASELINE.json configs)
-        if (a.n == 20) return launch_flow_kernel(ff::flow_kernel_eloc_static<20, 1>, a, threads, smem, st);
+        if (a.n == 20) {
+            constexpr int t1 = ff::flow_geom(ff::MODE_ELOC, 20, true).threads1;
+            if (threads == t1 + 32) return launch_flow_kernel(ff::flow_kernel_eloc_static<20, 1, 1>, a, threads, smem, st);
+            if (threads == t1) return launch_flow_kernel(ff::flow_kernel_eloc_static<20, 1, 0>, a, threads, smem, st);
+        }
     }
     if constexpr (MODE != ff::MODE_ELOC) {
         if (threads <= 256 && getenv("FF_FLOW_BIG") == nullptr)
@@ -218,7 +262,9 @@ int launch_eloc2(ff::FlowArgs& a, cudaStream_t st) {
 // barrier-synchronous) 185 ms, against 177 ms of the default flow_kernel_eloc_static.
 int try_eloc_pipeline(ff::FlowArgs& a, cudaStream_t st) {
     if (getenv("FF_ELOC_V3") != nullptr && a.H_mu > 0 && a.n == 20) return launch_eloc3<20, 1>(a, st);
-    if (getenv("FF_ELOC_V2") != nullptr && a.H_mu > 0 && a.n == 20) return launch_eloc2<20, 1>(a, st);
+    // opt-in fused-phase kernel (FF_ELOC_V2=1): 109 ms with the Taylor tables against 86 ms of flow_kernel_eloc_static
+    const bool v2 = getenv("FF_ELOC_V2") != nullptr;
+    if (v2 && a.H_mu > 0 && a.n == 20) return launch_eloc2<20, 1>(a, st);
     return 1;
 }
 
@@ -246,6 +292,8 @@ int ff_cnf_generate(const ff_model* m, const double* z, long long B, int reverse
     if (int e = plan_flow(ff::MODE_V, m, a, threads, smem)) return e;
     a.ta = reverse ? m->t1 : m->t0; a.tb = reverse ? m->t0 : m->t1;
     a.B = B; a.x_in = z; a.y_out = x;
+    RadialTables rt;
+    if (int e = rt.build(m, (cudaStream_t)stream, a)) return e;
     return launch_flow<ff::MODE_V>(a, threads, smem, (cudaStream_t)stream);
 }
 
@@ -262,6 +310,8 @@ int ff_cnf_delta_logp(const ff_model* m, const double* x, long long B, double* z
     a.ta = m->t1; a.tb = m->t0;
     a.B = B; a.x_in = x; a.y_out = z; a.delta_out = delta_logp;
     a.stash_y = stash_y; a.stash_c = stash_c;
+    RadialTables rt;
+    if (int e = rt.build(m, (cudaStream_t)stream, a)) return e;
     return stash ? launch_flow<ff::MODE_STASH>(a, threads, smem, (cudaStream_t)stream)
                  : launch_flow<ff::MODE_DIV>(a, threads, smem, (cudaStream_t)stream);
 }
@@ -281,6 +331,8 @@ int ff_eloc(const ff_model* m, const double* x, long long B, const int* orb, con
     a.stash_y = stash_y; a.stash_c = stash_c;
     a.orb = orb; a.walker_state = walker_state; a.Z = Z; a.harmonic = harmonic;
     a.logp = logp; a.grad = grad; a.lap = lap; a.kin = kinetic; a.pot = potential; a.eloc = eloc;
+    RadialTables rt;
+    if (int e = rt.build(m, (cudaStream_t)stream, a)) return e;
     {
         ff::FlowArgs a2 = a;
         const int r = try_eloc_pipeline(a2, (cudaStream_t)stream);

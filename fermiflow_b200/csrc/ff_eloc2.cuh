@@ -415,7 +415,14 @@ eloc2_kernel(const FlowArgs a) {
             double* Jn = S + (cur ? G_.oJ0 : G_.oJ1);
             const double* Lc = S + (cur ? G_.oL1 : G_.oL);
             double* Ln = S + (cur ? G_.oL : G_.oL1);
-            // ======== phase A: radial MLPs on the item warps, Gram matrix on the helper ==========
+            // ======== phase A: Gram matrix (tensor cores, all warps), radial functions per item ==
+            // With the Taylor tables the radial functions cost ~70 instructions per item, so the Gram
+            // matrix is shared by every warp; without them (fallback) the helper warp still overlaps it.
+            const bool tables = a.rt_eta != nullptr;
+            if (tables) phase_gram<SN, SMU>(AM, Jc, warp, nwarp, lane);
+            else if (warp >= IW) phase_gram<SN, SMU>(AM, Jc, warp - IW, HW, lane);
+            if (a.stash_y != nullptr && warp >= IW)
+                for (int e = tid - 32 * IW; e < D; e += 32 * HW) a.stash_y[(b * NS + stage) * D + e] = S[e];
             double rx = 0, ry = 0, ca = 0, cb_ = 0, ccq = 0, ceq = 0, cf = 0;
             if (warp < IW) {
                 const double* y = S;
@@ -426,7 +433,12 @@ eloc2_kernel(const FlowArgs a) {
                 const double d = d2 * inv_d;
                 double f[4];
                 FF_TICK2(1);
-                radial_mlp_n<3, NI>(it_pair ? coef_eta : coef_mu, it_pair ? a.H_eta : a.H_mu, d, tabl, f);
+                const bool hit = radial_table_eval<3>(it_pair ? a.rt_eta : a.rt_mu, d, f);
+                if (__any_sync(0xffffffffu, !hit)) {            // rare: outside the table -> direct sums (whole warp)
+                    double g[4];
+                    radial_mlp_n<3, NI>(it_pair ? coef_eta : coef_mu, it_pair ? a.H_eta : a.H_mu, d, tabl, g);
+                    if (!hit) { f[0] = g[0]; f[1] = g[1]; f[2] = g[2]; f[3] = g[3]; }
+                }
                 FF_TICK2(2);
                 if (it_valid) {
                     if (a.stash_c != nullptr) {
@@ -449,10 +461,6 @@ eloc2_kernel(const FlowArgs a) {
                     Grec[9] = ca * rx * ry;
                     Grec[10] = fma(ca * ry, ry, cf);
                 }
-            } else {
-                if (a.stash_y != nullptr)
-                    for (int e = tid - 32 * IW; e < D; e += 32 * HW) a.stash_y[(b * NS + stage) * D + e] = S[e];
-                phase_gram<SN, SMU>(AM, Jc, warp - IW, HW, lane);
             }
             FF_TICK2(3);
             __syncthreads();

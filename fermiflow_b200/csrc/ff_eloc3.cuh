@@ -164,7 +164,14 @@ eloc3_kernel(const FlowArgs a) {
 #ifdef FF_EXP_NO_MLP
             f[0] = d; f[1] = 0.5 * d; f[2] = 0.25 * d; f[3] = 0.125 * d;
 #else
-            radial_mlp_n<3, NI>(my_coef, HH, d, tabl, f);
+            {
+                const bool hit = kPipeTPI == 1 && radial_table_eval<3>(it_pair ? a.rt_eta : a.rt_mu, d, f);
+                if (__any_sync(0xffffffffu, !hit)) {
+                    double g[4];
+                    radial_mlp_n<3, NI>(my_coef, HH, d, tabl, g);
+                    if (!hit) { f[0] = g[0]; f[1] = g[1]; f[2] = g[2]; f[3] = g[3]; }
+                }
+            }
 #endif
             FF_TICK2(2);
             if (kPipeTPI == 2) {

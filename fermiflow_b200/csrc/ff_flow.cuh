@@ -10,6 +10,7 @@
 #pragma once
 #include "ff_common.cuh"
 #include "ff_slater.cuh"
+#include "ff_radial_table.cuh"
 
 namespace ff {
 
@@ -26,6 +27,7 @@ struct FlowArgs {
     // model
     int n, n_up, H_eta, H_mu;
     const double *eta_w1, *eta_b1, *eta_w2, *mu_w1, *mu_b1, *mu_w2;
+    const double *rt_eta, *rt_mu;   // certified Taylor tables of eta / mu (ff_radial_table.cuh), nullable
     double ta, tb;          // integrate from ta to tb
     int nsteps;
     // batch
@@ -336,14 +338,14 @@ __device__ void eloc_finale(const FlowArgs& a, long long base, double* wbase,
 // SN > 0 fixes the particle number (and SMU the presence of the one-body MLP) at compile time:
 // every loop bound, offset and index division below then folds to a constant and the short
 // latency-bound phases unroll.  SN = 0 is the generic run-time version.
-template <int MODE, int SN, int SMU>
+template <int MODE, int SN, int SMU, int HELP = 1>
 __device__ __forceinline__ void flow_body(const FlowArgs& a) {
     extern __shared__ __align__(16) double smem[];
     constexpr bool kS = SN > 0;
     constexpr FlowGeom GS = flow_geom(MODE, kS ? SN : 2, SMU != 0);
     // one extra "helper" warp (when the launch provides it) computes the Gram matrix while the
     // item warps are still in the MLP loop
-    const int tid = threadIdx.x, T = kS ? GS.threads1 + 32 : (int)blockDim.x;
+    const int tid = threadIdx.x, T = kS ? GS.threads1 + 32 * HELP : (int)blockDim.x;
     const int n = kS ? GS.n : a.n, D = kS ? GS.D : a.D, DP = kS ? GS.DP : a.DP, P = kS ? GS.P : a.P;
     const int NP = kS ? GS.NP : a.NP, W = kS ? 1 : a.W, NSV = kS ? GS.NSV : a.NSV;
     const int off_G = kS ? GS.off_G : a.off_G, off_AM = kS ? GS.off_AM : a.off_AM, off_u = kS ? GS.off_u : a.off_u;
@@ -441,7 +443,8 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
                 double f[4];
                 constexpr int ORD = (MODE == MODE_V) ? 0 : (MODE == MODE_DIV) ? 1 : (MODE == MODE_STASH) ? 2 : 3;
                 // one call for both item kinds: no divergence between pair and single lanes
-                radial_mlp<ORD>(it_pair ? coef_eta : coef_mu, it_pair ? a.H_eta : a.H_mu, d, tabl, f);
+                if (!radial_table_eval<ORD>(it_pair ? a.rt_eta : a.rt_mu, d, f))
+                    radial_mlp<ORD>(it_pair ? coef_eta : coef_mu, it_pair ? a.H_eta : a.H_mu, d, tabl, f);
                 constexpr int GR = (MODE == MODE_ELOC) ? kGRec : 3;
                 constexpr int GQ = (MODE == MODE_ELOC) ? 6 : 2;
                 double* G = myS + off_G + it_p * GR;
@@ -757,7 +760,9 @@ template <int MODE>
 __global__ void __launch_bounds__(256, 4) flow_kernel_small(const FlowArgs a) { flow_body<MODE, 0, 0>(a); }
 
 // Statically specialised E_loc sweep (one walker per CTA, two CTAs per SM).
-template <int SN, int SMU>
-__global__ void __launch_bounds__(256, 2) flow_kernel_eloc_static(const FlowArgs a) { flow_body<MODE_ELOC, SN, SMU>(a); }
+// HELP = 1: one extra helper warp computes the Gram matrix while the item warps run the MLP loop (direct
+// evaluation); HELP = 0: every warp shares the Gram matrix (Taylor tables: the item phase is short).
+template <int SN, int SMU, int HELP = 1>
+__global__ void __launch_bounds__(256, 2) flow_kernel_eloc_static(const FlowArgs a) { flow_body<MODE_ELOC, SN, SMU, HELP>(a); }
 
 }  // namespace ff

@@ -120,7 +120,17 @@ __global__ void __launch_bounds__(256, FF_WARP_MINB) flow_warp_kernel(const Flow
                     rx[k] = Y[2 * i] - Y[2 * j]; ry[k] = Y[2 * i + 1] - Y[2 * j + 1];
                     d[k] = sqrt(fma(rx[k], rx[k], ry[k] * ry[k]));
                 }
-                radial_mlp_items<ORD, NI>(coef_eta, a.H_eta, d, tabl, f);
+                {
+                    bool hit = true;
+#pragma unroll
+                    for (int k = 0; k < NI; ++k) {
+                        double g[4];
+                        const bool hk = radial_table_eval<ORD>(a.rt_eta, d[k], g);
+                        f[k][0] = g[0]; f[k][1] = g[1]; f[k][2] = g[2];
+                        hit = hit && (hk || !ok[k]);
+                    }
+                    if (__any_sync(0xffffffffu, !hit)) radial_mlp_items<ORD, NI>(coef_eta, a.H_eta, d, tabl, f);   // direct sums
+                }
 #pragma unroll
                 for (int k = 0; k < NI; ++k) {
                     const int p = p0 + 32 * k;
@@ -142,7 +152,12 @@ __global__ void __launch_bounds__(256, FF_WARP_MINB) flow_warp_kernel(const Flow
                     const int i = ok ? i0 : 0;
                     rx[0] = Y[2 * i]; ry[0] = Y[2 * i + 1];
                     d[0] = sqrt(fma(rx[0], rx[0], ry[0] * ry[0]));
-                    radial_mlp_items<ORD, 1>(coef_mu, a.H_mu, d, tabl, f);
+                    {
+                        double g[4];
+                        const bool hit = radial_table_eval<ORD>(a.rt_mu, d[0], g) || !ok;
+                        f[0][0] = g[0]; f[0][1] = g[1]; f[0][2] = g[2];
+                        if (__any_sync(0xffffffffu, !hit)) radial_mlp_items<ORD, 1>(coef_mu, a.H_mu, d, tabl, f);
+                    }
                     if (ok) {
                         *reinterpret_cast<double2*>(G + 2 * (NP + i)) = make_double2(f[0][0] * rx[0], f[0][0] * ry[0]);
                         if (ORD >= 1) qsum += fma(f[0][1], d[0], 2.0 * f[0][0]);
