@@ -481,3 +481,45 @@ def test_metropolis_kernels_bit_identical(dev, nup, ndn):
             outs.append(ff.sample(ho.orbitals[:nup], ho.orbitals[:ndn], (1000,), equilibrim_steps=40))
     assert torch.equal(outs[0], outs[1])
     assert torch.isfinite(outs[0]).all()
+
+
+# ---------------------------------------------------------------------------------------
+# Taylor tables of the radial functions (ff_radial_table.cuh) against the direct evaluation.
+
+def _sweeps(model, z):
+    x = model.cnf.generate(z)
+    zz, dl = model.cnf.delta_logp(x)
+    r = model.local_energy(x, stash=True)
+    return dict(x=x, z=zz, dl=dl, logp=r.logp, grad=r.grad, lap=r.lap, eloc=r.eloc, sc=r.stash.c)
+
+
+@pytest.mark.parametrize("case", ["bench", "sharp", "too_sharp", "zero", "far"])
+def test_radial_tables_match_direct_evaluation(dev, case):
+    """Every sweep with the certified Taylor tables (default) against the direct sum over hidden units
+    (FF_NO_TABLE=1).  sharp: max|w1| = 12 (0.008 node spacing); too_sharp: max|w1| = 60, the table does not
+    fit and every lane falls back; zero: all-zero MLPs; far: walkers beyond the tabulated range (d > 24)."""
+    from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
+    gen = torch.Generator().manual_seed(31)
+    H = 24
+    eta, mu = MLP(1, H), MLP(1, H)
+    scale = {"bench": 1.0, "sharp": 4.0, "too_sharp": 20.0, "zero": 0.0, "far": 1.0}[case]
+    with torch.no_grad():
+        for m in (eta, mu):
+            m.fc1.weight.copy_(scale * torch.randn(H, 1, generator=gen))
+            m.fc1.bias.copy_(torch.randn(H, generator=gen) * (scale > 0))
+            m.fc2.weight.copy_(2e-2 * torch.randn(1, H, generator=gen) * (scale > 0))
+        if case == "sharp":
+            eta.fc1.weight[0, 0] = 12.0
+        if case == "too_sharp":
+            eta.fc1.weight[0, 0] = 60.0
+    cnf = CNF(Backflow(eta.to(dev), mu=mu.to(dev)), (0.0, 1.0), nsteps=6)
+    model = GSVMC(10, 10, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(2.0), sp_potential=HO()).to(dev)
+    z = model.basedist.sample(model.orbitals_up, model.orbitals_down, (300,))
+    if case == "far":
+        z = z.clone(); z[::7, 3, 0] += 27.0          # one particle outside the table range (pair distances > 24)
+    with _env(FF_NO_TABLE="1"):
+        ref = _sweeps(model, z)
+    got = _sweeps(model, z)
+    for k in ref:
+        close(got[k], ref[k], 2e-12, 1e-13)
+    assert all(torch.isfinite(v).all() for v in got.values())
