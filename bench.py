@@ -76,12 +76,17 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons}
 
 
-def flops_per_walker_eloc(n, H_eta, H_mu, ode_steps):
-    """Algorithmic FP64 flop count of one E_loc sweep per walker (kernel K_eloc):
-    per RK stage, items x hidden x 43 flop (sigmoid 25, pre-activation 2, three derivative
-    factors 8, four accumulations 8) + Jacobian GEMM 2 D^3 + Gram matrix 4 n (n+1) D / 2 * 2."""
+def flops_per_walker_eloc(n, H_eta, H_mu, ode_steps, tables=True):
+    """FP64 flop count of one E_loc sweep per walker (kernel `ff_eloc`).
+    Per RK stage: radial functions of the P items + Jacobian GEMM 2 D^3 + Gram matrix 4 n (n+1) D +
+    mat-vecs 4 D^2 + gather 22 n (n-1) + RK update 6 D^2.
+    tables=True  (what the kernel executes): certified degree-11 Taylor tables, 88 flop (Horner for f and
+                 its three derivatives) + 70 flop of geometry per item;
+    tables=False (reference formulation, FF_NO_TABLE=1): 43 flop per item AND hidden unit (sigmoid 21,
+                 pre-activation 2, three derivative factors 8, four accumulations 8, geometry amortised)."""
     D, NP = 2 * n, n * (n - 1) // 2
-    per_stage = 43 * (NP * H_eta + n * H_mu) + 2 * D ** 3 + 4 * n * (n + 1) * D
+    items = (88 + 70) * (NP + (n if H_mu else 0)) if tables else 43 * (NP * H_eta + n * H_mu)
+    per_stage = items + 2 * D ** 3 + 4 * n * (n + 1) * D + 4 * D * D + 22 * n * (n - 1) + 6 * D * D
     return 4 * ode_steps * per_stage
 
 
@@ -226,7 +231,9 @@ def run_ours(args):
     total_walkers = B * world * args.steps
     value = total_walkers / (ms * 1e-3)
     n = args.nup + args.ndown
-    fl = flops_per_walker_eloc(n, args.hidden, args.hidden, args.ode_steps) * B
+    tables_on = os.environ.get("FF_NO_TABLE") is None
+    fl = flops_per_walker_eloc(n, args.hidden, args.hidden, args.ode_steps, tables=tables_on) * B
+    fl_ref = flops_per_walker_eloc(n, args.hidden, args.hidden, args.ode_steps, tables=False) * B
     by = hbm_bytes_per_walker_eloc(n, True, args.ode_steps) * B
     peaks = {}
     try:
@@ -251,6 +258,10 @@ def run_ours(args):
         "roofline": {"bound": "fp64", "kernel": "ff::flow_kernel_eloc_static<20,1> (E_loc sweep)", "achieved": fl / (eloc_ms * 1e-3) / 1e12,
                      "peak": peak.value / 1e12, "unit": "TFLOP/s", "frac": fl / (eloc_ms * 1e-3) / peak.value,
                      "peak_source": "ff_fp64_peak DFMA microbenchmark on this device (MEASURED_PEAKS.json has no fp64 entry)",
+                     "flops_counted": "executed formulation (radial functions from certified Taylor tables)" if tables_on
+                                      else "reference formulation (every hidden unit evaluated)",
+                     "reference_formulation": {"tflops_equivalent": fl_ref / (eloc_ms * 1e-3) / 1e12,
+                                               "frac_equivalent": fl_ref / (eloc_ms * 1e-3) / peak.value},
                      # ncu --set full (profiles/r01_eloc_ncu_full.md): 2.80 GB DRAM traffic for 8288 walkers
                      "traffic": 2.80e9 / 8288 * B if (n == 20 and args.hidden == 50 and args.ode_steps == 16) else None,
                      "traffic_source": "ncu dram__bytes_read+write, 8288-walker capture scaled per walker",
