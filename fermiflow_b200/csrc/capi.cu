@@ -262,8 +262,11 @@ int launch_eloc2(ff::FlowArgs& a, cudaStream_t st) {
 // barrier-synchronous) 185 ms, against 177 ms of the default flow_kernel_eloc_static.
 int try_eloc_pipeline(ff::FlowArgs& a, cudaStream_t st) {
     if (getenv("FF_ELOC_V3") != nullptr && a.H_mu > 0 && a.n == 20) return launch_eloc3<20, 1>(a, st);
-    // opt-in fused-phase kernel (FF_ELOC_V2=1): 109 ms with the Taylor tables against 86 ms of flow_kernel_eloc_static
-    const bool v2 = getenv("FF_ELOC_V2") != nullptr;
+    // With the Taylor tables the sweep is bound by the latency of the matrix phases and the fused-phase kernel
+    // with three helper warps wins (105 ms against 113 ms of flow_kernel_eloc_static at N = 20, 65536 walkers);
+    // with direct evaluation (FF_NO_TABLE=1) the 128-register static kernel does (177 ms against 185 ms).
+    // FF_ELOC_V1=1 / FF_ELOC_V2=1 force one or the other.
+    const bool v2 = getenv("FF_ELOC_V2") != nullptr || (a.rt_eta != nullptr && getenv("FF_ELOC_V1") == nullptr);
     if (v2 && a.H_mu > 0 && a.n == 20) return launch_eloc2<20, 1>(a, st);
     return 1;
 }

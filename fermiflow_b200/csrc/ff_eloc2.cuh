@@ -334,7 +334,7 @@ __host__ __device__ constexpr Eloc2Launch eloc2_launch(int n, bool has_mu) {
     const Eloc2Geom g = eloc2_geom(n, has_mu);
     q.item_warps = (g.P + 31) / 32;
 #ifndef FF_ELOC2_HELPERS
-#define FF_ELOC2_HELPERS 1
+#define FF_ELOC2_HELPERS 3
 #endif
     q.nwarp = q.item_warps + FF_ELOC2_HELPERS;
     if (q.nwarp < 4) q.nwarp = 4;
@@ -391,6 +391,7 @@ eloc2_kernel(const FlowArgs a) {
     const int it_j = it_pair ? pair_j[it_p] : it_i;
     double* const Grec = S + G_.off_G + it_p * kGRec;
     double* const AM = S + G_.off_AM;
+    const RtHeader my_rt = rt_load_header(it_pair ? a.rt_eta : a.rt_mu);     // Taylor table of this thread's radial function
 
 #ifdef FF_PHASE_TIMING
     __shared__ long long tsh[16];
@@ -433,7 +434,7 @@ eloc2_kernel(const FlowArgs a) {
                 const double d = d2 * inv_d;
                 double f[4];
                 FF_TICK2(1);
-                const bool hit = radial_table_eval<3>(it_pair ? a.rt_eta : a.rt_mu, d, f);
+                const bool hit = radial_table_eval<3>(my_rt, d, f);
                 if (__any_sync(0xffffffffu, !hit)) {            // rare: outside the table -> direct sums (whole warp)
                     double g[4];
                     radial_mlp_n<3, NI>(it_pair ? coef_eta : coef_mu, it_pair ? a.H_eta : a.H_mu, d, tabl, g);

@@ -398,6 +398,7 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
     const bool it_pair = it_p < NP;
     double* const myS = wbase + (size_t)(it_valid ? it_w : 0) * wstride;
     int it_i = 0, it_j = 0;
+    const RtHeader my_rt = rt_load_header(it_pair ? a.rt_eta : a.rt_mu);     // Taylor table of this thread's radial function
 
     for (long long base = (long long)blockIdx.x * W; base < a.B; base += (long long)gridDim.x * W) {
         __syncthreads();
@@ -443,7 +444,7 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
                 double f[4];
                 constexpr int ORD = (MODE == MODE_V) ? 0 : (MODE == MODE_DIV) ? 1 : (MODE == MODE_STASH) ? 2 : 3;
                 // one call for both item kinds: no divergence between pair and single lanes
-                if (!radial_table_eval<ORD>(it_pair ? a.rt_eta : a.rt_mu, d, f))
+                if (!radial_table_eval<ORD>(my_rt, d, f))
                     radial_mlp<ORD>(it_pair ? coef_eta : coef_mu, it_pair ? a.H_eta : a.H_mu, d, tabl, f);
                 constexpr int GR = (MODE == MODE_ELOC) ? kGRec : 3;
                 constexpr int GQ = (MODE == MODE_ELOC) ? 6 : 2;

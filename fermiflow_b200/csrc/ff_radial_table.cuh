@@ -139,17 +139,28 @@ __global__ void __launch_bounds__(128) radial_table_check_kernel(double* T0, dou
     }
 }
 
+// Table header in registers (loop invariant of a sweep: load it once per thread).
+struct RtHeader {
+    double inv_delta, delta;
+    const double* coef;        // nullptr: no usable table -> direct evaluation
+    int n_nodes;
+};
+__device__ __forceinline__ RtHeader rt_load_header(const double* __restrict__ T) {
+    RtHeader h;
+    h.inv_delta = 0.0; h.delta = 0.0; h.coef = nullptr; h.n_nodes = 0;
+    if (T != nullptr && __ldg(T + 3) != 0.0) {
+        h.inv_delta = __ldg(T); h.delta = __ldg(T + 1); h.n_nodes = (int)__ldg(T + 2); h.coef = T + kRtHeader;
+    }
+    return h;
+}
+
 // Table look-up.  Returns false when d is outside the table or the table is invalid / absent.
 template <int ORD>
-__device__ __forceinline__ bool radial_table_eval(const double* __restrict__ T, double d, double (&f)[4]) {
-    if (T == nullptr) return false;
-    const double inv_delta = __ldg(T), delta = __ldg(T + 1);
-    const int n_nodes = (int)__ldg(T + 2);
-    const bool valid = __ldg(T + 3) != 0.0;
-    const double kf = rint(d * inv_delta);
-    if (!valid || !(kf < (double)n_nodes) || !(kf >= 0.0)) return false;
-    const double t = fma(-kf, delta, d);
-    const double2* c2 = reinterpret_cast<const double2*>(T + kRtHeader + (size_t)(int)kf * kRtCoef);
+__device__ __forceinline__ bool radial_table_eval(const RtHeader& T, double d, double (&f)[4]) {
+    const double kf = rint(d * T.inv_delta);
+    if (T.coef == nullptr || !(kf < (double)T.n_nodes) || !(kf >= 0.0)) return false;
+    const double t = fma(-kf, T.delta, d);
+    const double2* c2 = reinterpret_cast<const double2*>(T.coef + (size_t)(int)kf * kRtCoef);
     double c[kRtCoef];
 #pragma unroll
     for (int q = 0; q < kRtCoef / 2; ++q) { const double2 v = __ldg(c2 + q); c[2 * q] = v.x; c[2 * q + 1] = v.y; }
@@ -163,6 +174,10 @@ __device__ __forceinline__ bool radial_table_eval(const double* __restrict__ T, 
     }
     f[0] = p0; f[1] = p1; f[2] = 2.0 * p2; f[3] = 6.0 * p3;
     return true;
+}
+template <int ORD>
+__device__ __forceinline__ bool radial_table_eval(const double* __restrict__ T, double d, double (&f)[4]) {
+    return radial_table_eval<ORD>(rt_load_header(T), d, f);
 }
 
 }  // namespace ff
