@@ -8,6 +8,7 @@
 
 #include "../../include/fermiflow_b200.h"
 #include "ff_adjoint.cuh"
+#include "ff_pgrad_binned.cuh"
 #include "ff_flow.cuh"
 #include "ff_flow_warp.cuh"
 #include "ff_eloc2.cuh"
