@@ -314,6 +314,113 @@ __device__ __forceinline__ void phase_gram(double* AM, const double* Jn, int mwa
 }
 
 
+// Ordered shared-memory load / tensor-core product (volatile asm keeps the program order): ptxas otherwise sinks
+// every operand load right in front of its DMMA and each product waits ~30 cycles for its own LDS.
+__device__ __forceinline__ double lds_ordered(const double* p) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+__device__ __forceinline__ void dmma_ordered(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// ---- tensor-core phases with operand reuse and many independent chains per warp ---------------------------------
+// J' = A J, column-block ownership: warp cb < NB keeps the B fragments of column block cb in registers and runs the
+// NB row blocks interleaved (2 NB accumulator chains: consecutive products of one chain are 2 NB issue slots apart,
+// more than the ~150-cycle latency of a dependent DMMA), RK update of each 8x8 block in the epilogue.
+template <int SN, int SMU>
+__device__ __forceinline__ void phase_aj_cols(double* S, const double* AM, const double* Jc, double* Jn, int sub, double h,
+                                              int cb, int lane) {
+    constexpr Eloc2Geom G_ = eloc2_geom(SN, SMU != 0);
+    constexpr int D = G_.D, D8 = G_.D8, DP = G_.DP, NB = G_.NB, KS = D8 / 4;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    double bf[KS];
+    const double* Bp = Jc + t4 * DP + 8 * cb + g8;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) bf[k] = lds_ordered(Bp + 4 * k * DP);
+    double acc[NB][2][2];
+#pragma unroll
+    for (int rb = 0; rb < NB; ++rb) { acc[rb][0][0] = acc[rb][0][1] = acc[rb][1][0] = acc[rb][1][1] = 0.0; }
+    const double* Ap = AM + g8 * DP + t4;
+    double af[NB], an[NB];                     // A fragments of k-step k and k + 1 (software pipeline over the LDS latency)
+#pragma unroll
+    for (int rb = 0; rb < NB; ++rb) { af[rb] = lds_ordered(Ap + 8 * rb * DP); an[rb] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        if (k + 1 < KS) {
+#pragma unroll
+            for (int rb = 0; rb < NB; ++rb) an[rb] = lds_ordered(Ap + 8 * rb * DP + 4 * (k + 1));
+        }
+#pragma unroll
+        for (int rb = 0; rb < NB; ++rb) dmma_ordered(acc[rb][k & 1][0], acc[rb][k & 1][1], af[rb], bf[k]);
+#pragma unroll
+        for (int rb = 0; rb < NB; ++rb) af[rb] = an[rb];
+    }
+    const int c = 8 * cb + 2 * t4;
+#pragma unroll
+    for (int rb = 0; rb < NB; ++rb) {
+        const int r = 8 * rb + g8;
+        if (r < D && c < D) {
+            const int idx = r * DP + c;
+            const double2 s = *reinterpret_cast<const double2*>(Jc + idx);
+            double2 Bv = make_double2(0.0, 0.0), Cv = make_double2(0.0, 0.0);
+            if (sub != 0) {
+                if (sub != 3) Bv = *reinterpret_cast<const double2*>(S + G_.oPB + idx);
+                Cv = *reinterpret_cast<const double2*>(S + G_.oPC + idx);
+            }
+            double2 sn;
+            sn.x = rk_elem(sub, s.x, h * (acc[rb][0][0] + acc[rb][1][0]), Bv.x, Cv.x);
+            sn.y = rk_elem(sub, s.y, h * (acc[rb][0][1] + acc[rb][1][1]), Bv.y, Cv.y);
+            *reinterpret_cast<double2*>(Jn + idx) = sn;
+            if (sub < 2) *reinterpret_cast<double2*>(S + G_.oPB + idx) = Bv;
+            if (sub < 3) *reinterpret_cast<double2*>(S + G_.oPC + idx) = Cv;
+        }
+    }
+}
+
+// M = J J^T: the ntri upper blocks are dealt to MW warps, NBW = ceil(ntri / MW) blocks per warp processed interleaved
+// (2 NBW accumulator chains per warp).
+template <int SN, int SMU, int MW>
+__device__ __forceinline__ void phase_gram_multi(double* AM, const double* Jn, int mwarp, int lane) {
+    constexpr Eloc2Geom G_ = eloc2_geom(SN, SMU != 0);
+    constexpr int D8 = G_.D8, DP = G_.DP, NB = G_.NB, KS = D8 / 4, NBW = (G_.ntri + MW - 1) / MW;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const double* Ar[NBW]; const double* Br[NBW]; double* Mo[NBW]; bool on[NBW];
+#pragma unroll
+    for (int q = 0; q < NBW; ++q) {
+        const int blk = mwarp + q * MW;
+        on[q] = blk < G_.ntri;
+        int rb = 0, rem = on[q] ? blk : 0;
+        while (rem >= NB - rb) { rem -= NB - rb; ++rb; }
+        const int cb = rb + rem;
+        Ar[q] = Jn + (8 * rb + g8) * DP + t4;
+        Br[q] = Jn + (8 * cb + g8) * DP + t4;
+        Mo[q] = AM + (8 * rb + g8) * DP + 8 * cb + 2 * t4;
+    }
+    double acc[NBW][2][2];
+#pragma unroll
+    for (int q = 0; q < NBW; ++q) { acc[q][0][0] = acc[q][0][1] = acc[q][1][0] = acc[q][1][1] = 0.0; }
+    double fa[NBW], fb[NBW], na[NBW], nb[NBW];
+#pragma unroll
+    for (int q = 0; q < NBW; ++q) { fa[q] = lds_ordered(Ar[q]); fb[q] = lds_ordered(Br[q]); na[q] = nb[q] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        if (k + 1 < KS) {
+#pragma unroll
+            for (int q = 0; q < NBW; ++q) { na[q] = lds_ordered(Ar[q] + 4 * (k + 1)); nb[q] = lds_ordered(Br[q] + 4 * (k + 1)); }
+        }
+#pragma unroll
+        for (int q = 0; q < NBW; ++q) dmma_ordered(acc[q][k & 1][0], acc[q][k & 1][1], fa[q], fb[q]);
+#pragma unroll
+        for (int q = 0; q < NBW; ++q) { fa[q] = na[q]; fb[q] = nb[q]; }
+    }
+#pragma unroll
+    for (int q = 0; q < NBW; ++q)
+        if (on[q]) *reinterpret_cast<double2*>(Mo[q]) = make_double2(acc[q][0][0] + acc[q][1][0], acc[q][0][1] + acc[q][1][1]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Barrier-synchronous E_loc sweep built from the phases above: one walker per CTA, one thread per
 // item (ceil(P/32) item warps) plus ONE helper warp that computes the Gram matrix while the item
@@ -420,8 +527,8 @@ eloc2_kernel(const FlowArgs a) {
             // With the Taylor tables the radial functions cost ~70 instructions per item, so the Gram
             // matrix is shared by every warp; without them (fallback) the helper warp still overlaps it.
             const bool tables = a.rt_eta != nullptr;
-            if (tables) phase_gram<SN, SMU>(AM, Jc, warp, nwarp, lane);
-            else if (warp >= IW) phase_gram<SN, SMU>(AM, Jc, warp - IW, HW, lane);
+            (void)tables;
+            if (warp >= IW) phase_gram_multi<SN, SMU, HW>(AM, Jc, warp - IW, lane);      // helper warps, while the items are evaluated
             if (a.stash_y != nullptr && warp >= IW)
                 for (int e = tid - 32 * IW; e < D; e += 32 * HW) a.stash_y[(b * NS + stage) * D + e] = S[e];
             double rx = 0, ry = 0, ca = 0, cb_ = 0, ccq = 0, ceq = 0, cf = 0;
@@ -501,9 +608,15 @@ eloc2_kernel(const FlowArgs a) {
             __syncthreads();
             FF_TICK2(8);
             // ======== phase D: stage derivative with the RK update fused in ======================
-            phase_aj_rk<SN, SMU>(S, AM, Jc, Jn, sub, h, warp, nwarp, lane);
+            if (nwarp > G_.NB) {
+                // column-block owners run A.J, the remaining warps the vector part, side by side
+                if (warp < G_.NB) phase_aj_cols<SN, SMU>(S, AM, Jc, Jn, sub, h, warp, lane);
+                else phase_vec_rk<SN, SMU>(S, AM, Jc, Lc, Ln, sub, h, tid - 32 * G_.NB, NT - 32 * G_.NB, warp - G_.NB, nwarp - G_.NB, lane);
+            } else {
+                phase_aj_rk<SN, SMU>(S, AM, Jc, Jn, sub, h, warp, nwarp, lane);
+                phase_vec_rk<SN, SMU>(S, AM, Jc, Lc, Ln, sub, h, tid, NT, warp, nwarp, lane);
+            }
             FF_TICK2(9);
-            phase_vec_rk<SN, SMU>(S, AM, Jc, Lc, Ln, sub, h, tid, NT, warp, nwarp, lane);
             FF_TICK2(10);
             __syncthreads();
             FF_TICK2(11);
