@@ -27,7 +27,8 @@ namespace ff {
 constexpr int kPgMaxBins = 640;          // eta bins + mu bins = threads of the CTA (96 registers each)
 constexpr int kPgMom = 12;               // moments per weight (t^0 .. t^11): 48 accumulator registers per thread
 constexpr double kPgSpacing = 0.25;      // delta * max|w1|: truncation (0.125 / pi)^12 ~ 2e-17
-constexpr double kPgDmax = 24.0;
+constexpr double kPgDmax = 24.0;         // node range of the pair distances (beyond: direct evaluation in the kernel)
+constexpr double kPgDmaxMu = 12.0;       // node range of the distances from the trap centre
 constexpr double kPgMaxDelta = 0.25;
 constexpr int kPgHdr = 16;
 // work layout (doubles): hdr[kPgHdr] | mom[kPgMaxBins][2 kPgMom] | direct[3 (H_eta + H_mu)]
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(256) pgrad_bins_setup_kernel(const PGradBinArg
     const size_t total = pgrad_binned_work_doubles(Ht);
     for (size_t i = kPgHdr + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) a.work[i] = 0.0;
     if (blockIdx.x != 0) return;
-    double res[2][3];
+    double wmx[2];
     for (int f = 0; f < 2; ++f) {
         const int H = f ? a.H_mu : a.H_eta;
         const double* w1 = f ? a.mu_w1 : a.eta_w1;
@@ -61,15 +62,23 @@ __global__ void __launch_bounds__(256) pgrad_bins_setup_kernel(const PGradBinArg
         red[threadIdx.x] = wm;
         __syncthreads();
         for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]); __syncthreads(); }
-        wm = red[0];
+        wmx[f] = red[0];
         __syncthreads();
-        const double delta = fmin(kPgMaxDelta, kPgSpacing / fmax(wm, 1e-300));
-        const double nb = H > 0 ? ceil(kPgDmax / delta) + 1.0 : 0.0;
-        res[f][0] = 1.0 / delta; res[f][1] = delta; res[f][2] = isfinite(wm) ? nb : 1e9;
     }
     if (threadIdx.x == 0) {
-        for (int f = 0; f < 2; ++f) for (int q = 0; q < 3; ++q) hdr[3 * f + q] = res[f][q];
-        hdr[6] = (res[0][2] + res[1][2] <= (double)kPgMaxBins) ? 1.0 : 0.0;
+        // mu (distances from the trap centre, n records per walker-stage) gets the coarsest admissible nodes over
+        // [0, kPgDmaxMu]; eta (pair distances, n (n-1) / 2 records) gets ALL remaining threads: finer nodes than the
+        // accuracy needs, so that the hottest bins hold fewer records (the bin walk is the critical path of a tile).
+        const double dm_max = fmin(kPgMaxDelta, kPgSpacing / fmax(wmx[1], 1e-300));
+        const double de_max = fmin(kPgMaxDelta, kPgSpacing / fmax(wmx[0], 1e-300));
+        const double nbm = a.H_mu > 0 ? ceil(kPgDmaxMu / dm_max) + 1.0 : 0.0;
+        const double nbe_min = ceil(kPgDmax / de_max) + 1.0;
+        const bool ok = isfinite(wmx[0]) && isfinite(wmx[1]) && nbm + nbe_min <= (double)kPgMaxBins;
+        const double nbe = ok ? (double)kPgMaxBins - nbm : nbe_min;
+        const double de = ok ? kPgDmax / (nbe - 1.0) : de_max;
+        hdr[0] = 1.0 / de; hdr[1] = de; hdr[2] = nbe;
+        hdr[3] = 1.0 / dm_max; hdr[4] = dm_max; hdr[5] = nbm;
+        hdr[6] = ok ? 1.0 : 0.0;
     }
 }
 
@@ -86,9 +95,9 @@ __global__ void __launch_bounds__(kPgMaxBins, 1) pgrad_binned_kernel(const PGrad
     const int REC = R * P;
     // shared carve-up
     double* tab = smem;                                   // kTabDoubles (direct evaluation of overflow records)
-    double* ysk = tab + kTabDoubles;                      // R x 2D
-    double* kdl = ysk + (size_t)R * 2 * D;                // R
-    double* rec_t = kdl + ((R + 1) & ~1);                 // REC each
+    double* ysk0 = tab + kTabDoubles;                     // 2 buffers of R x 2D (next tile arrives by cp.async)
+    double* kdl0 = ysk0 + (size_t)2 * R * 2 * D;          // 2 x R
+    double* rec_t = kdl0 + 2 * ((R + 1) & ~1);            // REC each
     double* rec_A = rec_t + REC;
     double* rec_B = rec_A + REC;
     int* cnt = reinterpret_cast<int*>(rec_B + REC);       // kPgMaxBins
@@ -100,7 +109,7 @@ __global__ void __launch_bounds__(kPgMaxBins, 1) pgrad_binned_kernel(const PGrad
     unsigned short* ovf = sorted + ((REC + 3) & ~3);
     unsigned char* pair_i = reinterpret_cast<unsigned char*>(ovf + ((REC + 3) & ~3));
     unsigned char* pair_j = pair_i + ((NP + 7) & ~7);
-    int* ovf_count = wsum + 32;
+    int* ovf_counts = wsum + 32;                          // one counter per tile parity
 
     fill_exp_table(tab);
     const double* tabl = tab + (tid & 15);
@@ -126,21 +135,36 @@ __global__ void __launch_bounds__(kPgMaxBins, 1) pgrad_binned_kernel(const PGrad
     const int my_bin = tid;
 
     const long long nrec = a.B * NS;
-    for (long long r0 = (long long)blockIdx.x * R; r0 < nrec; r0 += (long long)gridDim.x * R) {
+    // stage-input / adjoint rows of one tile, asynchronously (cp.async) into buffer `buf`
+    auto fetch_tile = [&](long long r0, int buf) {
+        if (r0 >= nrec) return;
         const int nr = (int)min((long long)R, nrec - r0);
-        __syncthreads();
+        double* yb = ysk0 + (size_t)buf * R * 2 * D;
         for (int g = tid; g < nr * 2 * D; g += T) {
             const int r = g / (2 * D), e = g - r * 2 * D;
-            ysk[g] = (e < D) ? a.stash_y[(r0 + r) * D + e] : a.kbar[(r0 + r) * D + e - D];
+            const double* src = (e < D) ? a.stash_y + (r0 + r) * D + e : a.kbar + (r0 + r) * D + e - D;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(yb + g)), "l"(src));
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        double* kb = kdl0 + buf * ((R + 1) & ~1);
         for (int r = tid; r < nr; r += T) {
             const long long rr = r0 + r;
             const long long b = rr / NS; const int stage = (int)(rr - b * NS), sb = stage & 3;
-            kdl[r] = a.gbar_delta[b] * a.h * ((sb == 0 || sb == 3) ? 0.125 : 0.375);
+            kb[r] = a.gbar_delta[b] * a.h * ((sb == 0 || sb == 3) ? 0.125 : 0.375);
         }
-        if (tid < nbins) { cnt[tid] = 0; cur[tid] = 0; }
-        if (tid == 0) *ovf_count = 0;
-        __syncthreads();
+    };
+    if (tid < nbins) { cnt[tid] = 0; cur[tid] = 0; }
+    if (tid < 2) ovf_counts[tid] = 0;
+    fetch_tile((long long)blockIdx.x * R, 0);
+    int buf = 0;
+    for (long long r0 = (long long)blockIdx.x * R; r0 < nrec; r0 += (long long)gridDim.x * R, buf ^= 1) {
+        const int nr = (int)min((long long)R, nrec - r0);
+        const double* ysk = ysk0 + (size_t)buf * R * 2 * D;
+        const double* kdl = kdl0 + buf * ((R + 1) & ~1);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                      // this tile has landed; the previous one is consumed
+        int* ovf_count = ovf_counts + buf;
+        if (tid == 0) ovf_counts[buf ^ 1] = 0;                // for the next tile (last read before the barrier above)
         // ---- records: d, weights, bin --------------------------------------------------------
         for (int g = tid; g < nr * P; g += T) {
             const int r = g / P, p = g - r * P;
@@ -176,6 +200,7 @@ __global__ void __launch_bounds__(kPgMaxBins, 1) pgrad_binned_kernel(const PGrad
             }
         }
         __syncthreads();
+        fetch_tile(r0 + (long long)gridDim.x * R, buf ^ 1);   // overlaps the scan, scatter and bin walk below
         // ---- exclusive scan of the bin counts ---------------------------------------------------
         {
             const int c = tid < nbins ? cnt[tid] : 0;
@@ -202,6 +227,7 @@ __global__ void __launch_bounds__(kPgMaxBins, 1) pgrad_binned_kernel(const PGrad
         // ---- every thread walks the records of ITS bin, two records in lock-step (the power chain is serial) ---
         if (my_bin < nbins) {
             const int p0 = off[my_bin], p1 = p0 + cnt[my_bin];
+            cnt[my_bin] = 0; cur[my_bin] = 0;                    // ready for the next tile (only the owner reads them now)
             int p = p0;
             for (; p + 2 <= p1; p += 2) {
                 const int g0 = sorted[p], g1 = sorted[p + 1];
