@@ -305,8 +305,8 @@ int ff_cnf_delta_logp(const ff_model* m, const double* x, long long B, double* z
                       double* stash_y, double* stash_c, void* stream) {
     if (int e = check_model(m)) return e;
     if (B < 0 || (B > 0 && !x)) return fail(-1, "ff_cnf_delta_logp: null input");
-    const bool stash = stash_y || stash_c;
-    if (stash && !(stash_y && stash_c)) return fail(-1, "ff_cnf_delta_logp: give both stash arrays or none");
+    const bool stash = stash_y != nullptr;
+    if (stash_c && !stash_y) return fail(-1, "ff_cnf_delta_logp: stash_c needs stash_y");
     ff::FlowArgs a{};
     int threads; size_t smem;
     const int mode = stash ? ff::MODE_STASH : ff::MODE_DIV;
@@ -326,7 +326,7 @@ int ff_eloc(const ff_model* m, const double* x, long long B, const int* orb, con
             double* stash_y, double* stash_c, void* stream) {
     if (int e = check_model(m)) return e;
     if (B < 0 || (B > 0 && (!x || !orb))) return fail(-1, "ff_eloc: null input");
-    if ((stash_y != nullptr) != (stash_c != nullptr)) return fail(-1, "ff_eloc: give both stash arrays or none");
+    if (stash_c && !stash_y) return fail(-1, "ff_eloc: stash_c needs stash_y");
     ff::FlowArgs a{};
     int threads; size_t smem;
     if (int e = plan_flow(ff::MODE_ELOC, m, a, threads, smem)) return e;

@@ -11,15 +11,34 @@
 //                    per hidden unit (column sums of the sigmoid matrix).
 #pragma once
 #include "ff_common.cuh"
+#include "ff_radial_table.cuh"
 
 namespace ff {
+
+// Direct radial function f, f', f'' from the parameter vectors in global memory (rare fallback of the adjoint
+// sweep when a distance is outside the Taylor table: plain exp(), no shared-memory tables).
+__device__ __noinline__ void radial_direct_global(const double* w1, const double* b1, const double* w2, int H, double d,
+                                                  double (&f)[4]) {
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+    for (int h = 0; h < H; ++h) {
+        const double w = w1[h];
+        const double s = 1.0 / (1.0 + exp(-fma(w, d, b1[h])));
+        const double s1 = fma(-s, s, s);
+        const double s2 = s1 * fma(-2.0, s, 1.0);
+        const double c = w2[h];
+        f0 = fma(c, s, f0); f1 = fma(c * w, s1, f1); f2 = fma(c * w * w, s2, f2);
+    }
+    f[0] = f0; f[1] = f1; f[2] = f2; f[3] = 0.0;
+}
 
 struct AdjArgs {
     int n, H_eta, H_mu, nsteps;
     double h;                       // signed step of the forward sweep
     long long B;
     const double* stash_y;          // [B][NS][D]
-    const double* stash_c;          // [B][NS][P][3]
+    const double* stash_c;          // [B][NS][P][3], or null: f, f', f'' are recomputed from the Taylor tables
+    const double *rt_eta, *rt_mu;   // Taylor tables (ff_radial_table.cuh), used when stash_c is null
+    const double *eta_w1, *eta_b1, *eta_w2, *mu_w1, *mu_b1, *mu_w2;
     const double* gbar_z;           // [B][D]
     const double* gbar_delta;       // [B]
     double* kbar;                   // [B][NS][D]
@@ -27,6 +46,8 @@ struct AdjArgs {
     int W, P, NP, D;
 };
 
+// RECOMPUTE = false: (f, f', f'') come from the stash (56 registers); true: recomputed from the Taylor tables.
+template <bool RECOMPUTE>
 __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, T = blockDim.x;
@@ -52,6 +73,7 @@ __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
     const int it_w = tid / P, it_p = tid - it_w * P;
     const bool it_valid = it_w < W, it_pair = it_p < NP;
     const double h = a.h;
+    const RtHeader my_rt = rt_load_header(RECOMPUTE ? (it_pair ? a.rt_eta : a.rt_mu) : nullptr);
 
     for (long long base = (long long)blockIdx.x * W; base < a.B; base += (long long)gridDim.x * W) {
         __syncthreads();
@@ -90,8 +112,10 @@ __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
                 long long b = base + it_w;
                 double f0 = 0, f1 = 0, f2 = 0, kd = 0;
                 if (b < a.B) {
-                    const double* sc = a.stash_c + ((b * NS + stage) * P + it_p) * 3;
-                    f0 = sc[0]; f1 = sc[1]; f2 = sc[2];
+                    if (!RECOMPUTE) {
+                        const double* sc = a.stash_c + ((b * NS + stage) * P + it_p) * 3;
+                        f0 = sc[0]; f1 = sc[1]; f2 = sc[2];
+                    }
                     kd = a.gbar_delta[b] * h * ((sub == 0 || sub == 3) ? 0.125 : 0.375);
                 }
                 const double* y = yy(it_w);
@@ -104,6 +128,14 @@ __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
                     rx = y[2 * it_i]; ry = y[2 * it_i + 1]; kx = k[2 * it_i]; ky = k[2 * it_i + 1];
                 }
                 const double d = sqrt(fma(rx, rx, ry * ry));
+                if (RECOMPUTE) {
+                    double f[4];
+                    if (!radial_table_eval<2>(my_rt, d, f)) {
+                        if (it_pair) radial_direct_global(a.eta_w1, a.eta_b1, a.eta_w2, a.H_eta, d, f);
+                        else radial_direct_global(a.mu_w1, a.mu_b1, a.mu_w2, a.H_mu, d, f);
+                    }
+                    f0 = f[0]; f1 = f[1]; f2 = f[2];
+                }
                 const double alpha = fma(kx, rx, ky * ry);
                 const double q1 = (it_pair ? 2.0 : 1.0) * fma(f2, d, 3.0 * f1);
                 const double c = (alpha * f1 - kd * q1) / d;

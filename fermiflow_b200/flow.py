@@ -3,6 +3,7 @@
 RK4 CUDA kernels (C ABI ff_cnf_generate / ff_cnf_delta_logp / ff_eloc / ff_logp_backward).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -25,7 +26,10 @@ class _Stash:
         L.check(L.lib().ff_stash_sizes(C.byref(model), B, C.byref(ny), C.byref(nc)))
         L.check(L.lib().ff_backward_work_size(C.byref(model), B, C.byref(nw)))
         self.y = torch.empty(ny.value, dtype=torch.float64, device=device)
-        self.c = torch.empty(nc.value, dtype=torch.float64, device=device)
+        # the per-item radial functions (f, f', f''): 16x the size of the stage inputs (22 GB for 65536 walkers at
+        # n = 20).  FF_NO_STASH_C=1 drops them: the backward sweep then recomputes them from the stage inputs
+        # (Taylor tables), which costs 28 ms more per iteration at that size but 16x less memory.
+        self.c = None if os.environ.get("FF_NO_STASH_C") else torch.empty(nc.value, dtype=torch.float64, device=device)
         self.n_work = nw.value
 
 

@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path (through the Python mirror -> C ABI) against the CPU
 oracle and the golden vectors produced by the real reference.  Tolerances: 1e-10 relative
 (BASELINE.json north_star) unless a looser, documented bound applies."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -490,7 +492,7 @@ def _sweeps(model, z):
     x = model.cnf.generate(z)
     zz, dl = model.cnf.delta_logp(x)
     r = model.local_energy(x, stash=True)
-    return dict(x=x, z=zz, dl=dl, logp=r.logp, grad=r.grad, lap=r.lap, eloc=r.eloc, sc=r.stash.c)
+    return dict(x=x, z=zz, dl=dl, logp=r.logp, grad=r.grad, lap=r.lap, eloc=r.eloc, sy=r.stash.y)
 
 
 @pytest.mark.parametrize("case", ["bench", "sharp", "too_sharp", "zero", "far"])
@@ -562,6 +564,45 @@ def test_binned_parameter_gradient_matches_direct(dev, case):
     with _env(FF_NO_BINNED_PGRAD="1"):
         ref = grads()
     got = grads()
+    for a, b in zip(got, ref):
+        assert torch.isfinite(a).all()
+        close(a, b, 1e-11, 1e-13 * float(max(r.abs().max() for r in ref)))
+
+
+@pytest.mark.parametrize("case", ["bench", "far", "too_sharp"])
+def test_backward_with_and_without_radial_stash(dev, case):
+    """ff_logp_backward reads the (f, f', f'') stash the forward sweep wrote (22 GB per 65536 walkers at n = 20);
+    with FF_NO_STASH_C=1 it recomputes them from the stage inputs.  Both must give the same gradients (far: distances
+    outside the Taylor table, too_sharp: no usable table -> direct sums in the adjoint sweep)."""
+    from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
+    gen = torch.Generator().manual_seed(91)
+    H = 16
+    eta, mu = MLP(1, H), MLP(1, H)
+    with torch.no_grad():
+        for m in (eta, mu):
+            m.fc1.weight.copy_(torch.randn(H, 1, generator=gen))
+            m.fc1.bias.copy_(torch.randn(H, generator=gen))
+            m.fc2.weight.copy_(2e-2 * torch.randn(1, H, generator=gen))
+        if case == "too_sharp":
+            mu.fc1.weight[3, 0] = 70.0
+    cnf = CNF(Backflow(eta.to(dev), mu=mu.to(dev)), (0.0, 1.0), nsteps=5)
+    model = GSVMC(10, 10, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(2.0), sp_potential=HO()).to(dev)
+    z = model.basedist.sample(model.orbitals_up, model.orbitals_down, (129,))
+    if case == "far":
+        z = z.clone(); z[::4, 7, 0] += 26.0
+    x = model.cnf.generate(z)
+    w = torch.randn(129, generator=gen).to(dev) / 129
+
+    def grads():
+        for p in model.parameters():
+            p.grad = None
+        xr = x.clone().requires_grad_(True)
+        lp = model.logp(xr, params_require_grad=True)
+        (lp * w).sum().backward()
+        return [xr.grad.clone()] + [p.grad.clone() for p in model.parameters()]
+    ref = grads()
+    with _env(FF_NO_STASH_C="1"):
+        got = grads()
     for a, b in zip(got, ref):
         assert torch.isfinite(a).all()
         close(a, b, 1e-11, 1e-13 * float(max(r.abs().max() for r in ref)))
