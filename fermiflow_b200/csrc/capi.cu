@@ -251,7 +251,7 @@ int launch_eloc2(ff::FlowArgs& a, cudaStream_t st) {
     a.off_G = g.off_G; a.off_AM = g.off_AM; a.off_u = g.off_u; a.off_kLx = g.off_kLx; a.off_part = g.off_part;
     a.off_x0 = g.off_x0; a.off_sl = g.off_sl; a.wstride = g.wstride; a.W = 1;
     const int need = ff::slater_scratch_size(a.n_up, a.n - a.n_up) + 2 * g.D + g.n * g.n + g.NP + 8;
-    if (need > 2 * g.MAT) return fail(-2, "internal: finale scratch does not fit");
+    if (need > 2 * g.MAT) return 1;            // e.g. all particles in one spin block: the generic kernel takes over
     constexpr int NI = FF_ELOC2_ILP;
     const int common = ff::kTabDoubles + 6 * (ff::coef_rows2<NI>(a.H_eta) + ff::coef_rows2<NI>(a.H_mu)) + 2 * ((g.NP + 7) / 8) + 2;
     const size_t smem = (size_t)(common + g.wstride) * 8;
@@ -268,7 +268,15 @@ int try_eloc_pipeline(ff::FlowArgs& a, cudaStream_t st) {
     // with direct evaluation (FF_NO_TABLE=1) the 128-register static kernel does (177 ms against 185 ms).
     // FF_ELOC_V1=1 / FF_ELOC_V2=1 force one or the other.
     const bool v2 = getenv("FF_ELOC_V2") != nullptr || (a.rt_eta != nullptr && getenv("FF_ELOC_V1") == nullptr);
-    if (v2 && a.H_mu > 0 && a.n == 20) return launch_eloc2<20, 1>(a, st);
+    if (v2 && a.H_mu > 0) {
+        // statically specialised particle numbers (BASELINE.json configs: N = 6, 12, 20)
+        switch (a.n) {
+            case 20: return launch_eloc2<20, 1>(a, st);
+            case 12: return launch_eloc2<12, 1>(a, st);
+            case 6: return launch_eloc2<6, 1>(a, st);
+            default: break;
+        }
+    }
     return 1;
 }
 

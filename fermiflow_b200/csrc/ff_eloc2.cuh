@@ -449,8 +449,13 @@ __host__ __device__ constexpr Eloc2Launch eloc2_launch(int n, bool has_mu) {
     return q;
 }
 
+// resident CTAs per SM the register allocation aims at: ~96 registers per thread (the matrix phases are latency bound,
+// warps per SM count), at least 2 where a CTA has at most 320 threads
+__host__ __device__ constexpr int eloc2_min_blocks(int threads) {
+    return threads > 320 ? 1 : (65536 / (96 * threads) < 2 ? 2 : (65536 / (96 * threads) > 8 ? 8 : 65536 / (96 * threads)));
+}
 template <int SN, int SMU>
-__global__ void __launch_bounds__(eloc2_launch(SN, SMU != 0).threads, (eloc2_launch(SN, SMU != 0).threads <= 320) ? 2 : 1)
+__global__ void __launch_bounds__(eloc2_launch(SN, SMU != 0).threads, eloc2_min_blocks(eloc2_launch(SN, SMU != 0).threads))
 eloc2_kernel(const FlowArgs a) {
     extern __shared__ __align__(16) double smem[];
     constexpr Eloc2Geom G_ = eloc2_geom(SN, SMU != 0);
