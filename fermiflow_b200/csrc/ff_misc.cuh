@@ -330,7 +330,8 @@ __device__ __forceinline__ double metro_logdet(const double* X, int xs, int i0, 
             A[(size_t)(r * ns + c) * sa] = inv_sqrt_pi * vx * vy;
         }
     }
-    double ld = 0.0;
+    // log|det| = log(prod of pivot mantissas) + (sum of pivot exponents) ln 2: one log per block instead of one per pivot
+    double prod = 1.0; int esum = 0;
     for (int k = 0; k < ns; ++k) {
         int p = k; double best = fabs(A[(size_t)(k * ns + k) * sa]);
         for (int r = k + 1; r < ns; ++r) {
@@ -344,7 +345,7 @@ __device__ __forceinline__ double metro_logdet(const double* X, int xs, int i0, 
                 A[(size_t)(p * ns + c) * sa] = t;
             }
         }
-        ld += log(best);
+        { int e; prod *= frexp(best, &e); esum += e; }
         const double ipv = 1.0 / A[(size_t)(k * ns + k) * sa];
         for (int r = k + 1; r < ns; ++r) {
             const double l = A[(size_t)(r * ns + k) * sa] * ipv;
@@ -352,7 +353,7 @@ __device__ __forceinline__ double metro_logdet(const double* X, int xs, int i0, 
                 A[(size_t)(r * ns + c) * sa] = fma(-l, A[(size_t)(k * ns + c) * sa], A[(size_t)(r * ns + c) * sa]);
         }
     }
-    return ld;
+    return log(prod) + esum * 0.69314718055994530942;
 }
 
 __global__ void __launch_bounds__(128) metropolis_kernel(const MetroArgs a) {
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(256) metropolis_warp_kernel(const MetroArgs a)
                 }
             }
             __syncwarp();
-            double ld = 0.0;
+            double prod = 1.0; int esum = 0;                          // same mantissa / exponent accumulation as metro_logdet
             for (int k = 0; k < nmax; ++k) {
                 const bool on = k < ns;                                // this half still has pivots to do
                 // pivot: first maximum of |A[r][k]|, r >= k, lane hl = row
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(256) metropolis_warp_kernel(const MetroArgs a)
                         A[k * LD + hl] = A[p * LD + hl];
                         A[p * LD + hl] = t;
                     }
-                    ld += log(best);
+                    { int e; prod *= frexp(best, &e); esum += e; }
                 }
                 __syncwarp();
                 if (on && hl > k && hl < ns) {                         // eliminate below the pivot, columns c > k
@@ -507,6 +508,7 @@ __global__ void __launch_bounds__(256) metropolis_warp_kernel(const MetroArgs a)
                 }
                 __syncwarp();
             }
+            const double ld = log(prod) + esum * 0.69314718055994530942;
             const double lu = __shfl_sync(0xffffffffu, ld, 0), ldn = __shfl_sync(0xffffffffu, ld, 16);
             return 2.0 * ((n_up ? lu : 0.0) + (n_dn ? ldn : 0.0));
         };
