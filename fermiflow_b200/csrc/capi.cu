@@ -254,8 +254,17 @@ int launch_eloc2(ff::FlowArgs& a, cudaStream_t st) {
     if (need > 2 * g.MAT) return 1;            // e.g. all particles in one spin block: the generic kernel takes over
     constexpr int NI = FF_ELOC2_ILP;
     const int common = ff::kTabDoubles + 6 * (ff::coef_rows2<NI>(a.H_eta) + ff::coef_rows2<NI>(a.H_mu)) + 2 * ((g.NP + 7) / 8) + 2;
-    const size_t smem = (size_t)(common + g.wstride) * 8;
+    size_t smem = (size_t)(common + g.wstride) * 8;
     if ((long long)smem > dev_info().smem_optin) return 1;
+    {   // what is left of this CTA's share of the SM mirrors the head of the eta table (96 bytes per node)
+        const DevInfo di = dev_info();
+        // ... without lowering the number of resident CTAs the register allocation aims at
+        const int occ = ff::eloc2_min_blocks(q.threads);
+        const long long share = (long long)di.smem_sm / occ - di.smem_reserved - 64;
+        const long long room = std::min<long long>(share, di.smem_optin) - (long long)smem;
+        a.rt_cache_nodes = (a.rt_eta != nullptr && room > 0) ? (int)std::min<long long>(room / (8 * ff::kRtCoef), 2048) : 0;
+        smem += (size_t)a.rt_cache_nodes * 8 * ff::kRtCoef;
+    }
     return launch_flow_kernel(ff::eloc2_kernel<SN, SMU>, a, q.threads, smem, st);
 }
 

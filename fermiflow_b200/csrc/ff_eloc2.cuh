@@ -492,6 +492,14 @@ eloc2_kernel(const FlowArgs a) {
         pair_j[p] = (unsigned char)(i + 1 + rem);
     }
     for (int e = tid; e < MAT; e += NT) { S[G_.oJ1 + e] = 0.0; S[G_.off_AM + e] = 0.0; }   // zero padding, once
+    // the first nodes of the eta table (short pair distances: most items) mirrored behind the walker block
+    double* rt_cache = S + G_.wstride;
+    int ncache = 0;
+    {
+        const RtHeader he = rt_load_header(a.rt_eta);
+        if (he.coef != nullptr) ncache = min(a.rt_cache_nodes, he.n_nodes);
+        for (int e = tid; e < ncache * kRtCoef; e += NT) rt_cache[e] = he.coef[e];
+    }
     __syncthreads();
 
     const double h = (a.tb - a.ta) / a.nsteps;
@@ -546,7 +554,7 @@ eloc2_kernel(const FlowArgs a) {
                 const double d = d2 * inv_d;
                 double f[4];
                 FF_TICK2(1);
-                const bool hit = radial_table_eval<3>(my_rt, d, f);
+                const bool hit = radial_table_eval_cached<3>(my_rt, rt_cache, it_pair ? ncache : 0, d, f);
                 if (__any_sync(0xffffffffu, !hit)) {            // rare: outside the table -> direct sums (whole warp)
                     double g[4];
                     radial_mlp_n<3, NI>(it_pair ? coef_eta : coef_mu, it_pair ? a.H_eta : a.H_mu, d, tabl, g);

@@ -28,6 +28,7 @@ struct FlowArgs {
     int n, n_up, H_eta, H_mu;
     const double *eta_w1, *eta_b1, *eta_w2, *mu_w1, *mu_b1, *mu_w2;
     const double *rt_eta, *rt_mu;   // certified Taylor tables of eta / mu (ff_radial_table.cuh), nullable
+    int rt_cache_nodes;             // nodes of the eta table a kernel may mirror in shared memory behind its walker block
     double ta, tb;          // integrate from ta to tb
     int nsteps;
     // batch
