@@ -3,7 +3,7 @@
 // The velocity field only ever evaluates f(d) = sum_h w2_h sigmoid(w1_h d + b1_h) (MLP.py:30-45 with
 // D_in = 1) and its d-derivatives at scalar distances.  f is analytic with its nearest singularity at
 // imaginary distance pi / max|w1| from the real axis, so a degree-11 Taylor polynomial around nodes
-// spaced delta = 0.1 / max|w1| reproduces f, f', f'', f''' to ~1e-15 .. 3e-14 relative (the rounding
+// spaced delta = 0.15 / max|w1| reproduces f, f', f'', f''' to ~1e-15 .. 3e-14 relative (the rounding
 // level of the direct sum): 44 FMAs per item instead of ~25 FP64 instructions per item AND hidden unit.
 //
 //   build    : every sweep launch rebuilds the tables from the current parameters (one tiny kernel):
@@ -23,7 +23,7 @@ constexpr int kRtDeg = 11;                 // Taylor degree
 constexpr int kRtCoef = kRtDeg + 1;        // doubles per node (96 bytes)
 constexpr int kRtMaxNodes = 8192;          // capacity per function
 constexpr int kRtHeader = 8;               // doubles: inv_delta, delta, n_nodes, valid, max|w1|, check, -, -
-constexpr double kRtSpacing = 0.1;         // delta * max|w1|
+constexpr double kRtSpacing = 0.15;        // delta * max|w1|
 constexpr double kRtDmax = 24.0;           // tabulated range of d
 constexpr double kRtMaxDelta = 0.125;
 __host__ __device__ constexpr size_t radial_table_doubles() { return kRtHeader + (size_t)kRtMaxNodes * kRtCoef; }
