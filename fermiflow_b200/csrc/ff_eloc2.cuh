@@ -616,7 +616,7 @@ eloc2_kernel(const FlowArgs a) {
                 *reinterpret_cast<double2*>(AM + j2 * DP + i2) = make_double2(a00, a01);
                 *reinterpret_cast<double2*>(AM + (j2 + 1) * DP + i2) = make_double2(a01, a11);
             }
-            phase_gather<SN, SMU>(S, AM, tid, NT);
+            phase_gather<SN, SMU>(S, AM, NT - 1 - tid, NT);      // sums dealt from the last thread down: the helper warps start at once, the item warps write their A blocks first
             FF_TICK2(7);
             __syncthreads();
             FF_TICK2(8);
