@@ -14,6 +14,7 @@
 #include "ff_eloc2.cuh"
 #include "ff_eloc3.cuh"
 #include "ff_misc.cuh"
+#include "ff_metro_reg.cuh"
 
 namespace {
 

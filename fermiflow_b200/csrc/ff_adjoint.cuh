@@ -87,8 +87,28 @@ __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
             ubar(w)[e] = (b < a.B) ? a.gbar_z[b * D + e] : 0.0;
         }
         __syncthreads();
+        // The stash of stage s - 1 is requested while stage s is being processed (its addresses do not depend on
+        // the sweep): pf_y = stage input of element g = tid, pf_c = (f, f', f'') of this thread's item.
+        double pf_y = 0.0, pf_c0 = 0.0, pf_c1 = 0.0, pf_c2 = 0.0;
+        const bool pf_has_y = tid < W * D && base + tid / D < a.B;
+        const bool pf_has_c = !RECOMPUTE && it_valid && base + it_w < a.B;
+        const double* pf_yp = a.stash_y + ((base + tid / D) * NS) * D + (tid - (tid / D) * D);
+        const double* pf_cp = RECOMPUTE ? nullptr : a.stash_c + ((base + it_w) * NS * P + it_p) * 3;
+        if (pf_has_y) pf_y = __ldcs(pf_yp + (size_t)(NS - 1) * D);
+        if (pf_has_c) {
+            const double* sc = pf_cp + (size_t)(NS - 1) * P * 3;
+            pf_c0 = __ldcs(sc); pf_c1 = __ldcs(sc + 1); pf_c2 = __ldcs(sc + 2);
+        }
         for (int stage = NS - 1; stage >= 0; --stage) {
             const int sub = stage & 3;
+            const double cur_y = pf_y, cur_c0 = pf_c0, cur_c1 = pf_c1, cur_c2 = pf_c2;
+            if (stage > 0) {
+                if (pf_has_y) pf_y = __ldcs(pf_yp + (size_t)(stage - 1) * D);
+                if (pf_has_c) {
+                    const double* sc = pf_cp + (size_t)(stage - 1) * P * 3;
+                    pf_c0 = __ldcs(sc); pf_c1 = __ldcs(sc + 1); pf_c2 = __ldcs(sc + 2);
+                }
+            }
             // stage adjoint kbar, stage input y
             for (int g = tid; g < W * D; g += T) {
                 int w = g / D, e = g - w * D;
@@ -102,7 +122,7 @@ __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
                 kb(w)[e] = k;
                 if (b < a.B) {
                     a.kbar[(b * NS + stage) * D + e] = k;
-                    yy(w)[e] = a.stash_y[(b * NS + stage) * D + e];
+                    yy(w)[e] = g == tid ? cur_y : a.stash_y[(b * NS + stage) * D + e];
                 } else {
                     yy(w)[e] = (double)(e >> 1) + 0.37 * (e & 1);
                 }
@@ -112,10 +132,7 @@ __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
                 long long b = base + it_w;
                 double f0 = 0, f1 = 0, f2 = 0, kd = 0;
                 if (b < a.B) {
-                    if (!RECOMPUTE) {
-                        const double* sc = a.stash_c + ((b * NS + stage) * P + it_p) * 3;
-                        f0 = sc[0]; f1 = sc[1]; f2 = sc[2];
-                    }
+                    if (!RECOMPUTE) { f0 = cur_c0; f1 = cur_c1; f2 = cur_c2; }
                     kd = a.gbar_delta[b] * h * ((sub == 0 || sub == 3) ? 0.125 : 0.375);
                 }
                 const double* y = yy(it_w);

@@ -476,13 +476,55 @@ def test_metropolis_kernels_bit_identical(dev, nup, ndn):
     from fermiflow_b200 import HO2D, FreeFermion
     ho = HO2D()
     outs = []
-    for env in (dict(FF_METRO_THREAD=None), dict(FF_METRO_THREAD="1")):
+    for env in (dict(FF_METRO_THREAD=None, FF_METRO_REG=None), dict(FF_METRO_THREAD="1", FF_METRO_REG=None),
+                dict(FF_METRO_THREAD=None, FF_METRO_REG="1")):
         with _env(**env):
             ff = FreeFermion(dev)
             ff.manual_seed(77)
             outs.append(ff.sample(ho.orbitals[:nup], ho.orbitals[:ndn], (1000,), equilibrim_steps=40))
     assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[2])      # register-resident sampler (ff_metro_reg.cuh)
     assert torch.isfinite(outs[0]).all()
+
+
+def test_metropolis_register_kernel_default_at_bench_size(dev):
+    """At >= 8192 walkers the register-resident sampler is the default; its chain equals the warp sampler's bit for
+    bit at the bench shape (10 up / 10 down, 100 moves) and for excited multi-state occupations."""
+    from fermiflow_b200 import HO2D, FreeFermion
+    ho = HO2D()
+    outs = []
+    for env in (dict(FF_METRO_WARP=None), dict(FF_METRO_WARP="1")):
+        with _env(**env):
+            ff = FreeFermion(dev)
+            ff.manual_seed(5)
+            outs.append(ff.sample(ho.orbitals[:10], ho.orbitals[:10], (8192 + 77,), equilibrim_steps=100))
+    assert torch.equal(outs[0], outs[1])
+    # excited determinants: orbitals of shells up to 5, different for every third walker
+    states = [(tuple(ho.orbitals[i] for i in up), tuple(ho.orbitals[i] for i in dn))
+              for up, dn in (([0, 1, 2, 3], [0, 1]), ([0, 2, 7, 20], [1, 27]), ([1, 5, 9, 14], [3, 35]))]
+    sidx = (torch.arange(9000) % 3).to(torch.int32).to(dev)
+    outs = []
+    for env in (dict(FF_METRO_WARP=None), dict(FF_METRO_WARP="1")):
+        with _env(**env):
+            ff = FreeFermion(dev)
+            ff.manual_seed(6)
+            outs.append(ff.sample_multstates(states, sidx, (9000,), equilibrim_steps=30))
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_metropolis_register_kernel_replay_vs_oracle(dev, O):
+    from fermiflow_b200 import HO2D, FreeFermion
+    ho = HO2D()
+    gen = torch.Generator().manual_seed(12)
+    B, nup, ndn, steps = 64, 3, 2, 25
+    x0 = torch.randn(B, nup + ndn, 2, generator=gen)
+    nrm = torch.randn(steps, B, nup + ndn, 2, generator=gen)
+    uni = torch.rand(steps, B, generator=gen)
+    ref = O.metropolis_sample(list(range(nup)), list(range(ndn)), x0, nrm, uni, tau=0.1)
+    with _env(FF_METRO_REG="1"):
+        x = FreeFermion(dev).sample(ho.orbitals[:nup], ho.orbitals[:ndn], (B,), equilibrim_steps=steps,
+                                    noise=(x0.to(dev), nrm.to(dev), uni.to(dev)))
+    close(x, ref, 1e-13)
 
 
 # ---------------------------------------------------------------------------------------
