@@ -87,28 +87,8 @@ __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
             ubar(w)[e] = (b < a.B) ? a.gbar_z[b * D + e] : 0.0;
         }
         __syncthreads();
-        // The stash of stage s - 1 is requested while stage s is being processed (its addresses do not depend on
-        // the sweep): pf_y = stage input of element g = tid, pf_c = (f, f', f'') of this thread's item.
-        double pf_y = 0.0, pf_c0 = 0.0, pf_c1 = 0.0, pf_c2 = 0.0;
-        const bool pf_has_y = tid < W * D && base + tid / D < a.B;
-        const bool pf_has_c = !RECOMPUTE && it_valid && base + it_w < a.B;
-        const double* pf_yp = a.stash_y + ((base + tid / D) * NS) * D + (tid - (tid / D) * D);
-        const double* pf_cp = RECOMPUTE ? nullptr : a.stash_c + ((base + it_w) * NS * P + it_p) * 3;
-        if (pf_has_y) pf_y = __ldcs(pf_yp + (size_t)(NS - 1) * D);
-        if (pf_has_c) {
-            const double* sc = pf_cp + (size_t)(NS - 1) * P * 3;
-            pf_c0 = __ldcs(sc); pf_c1 = __ldcs(sc + 1); pf_c2 = __ldcs(sc + 2);
-        }
         for (int stage = NS - 1; stage >= 0; --stage) {
             const int sub = stage & 3;
-            const double cur_y = pf_y, cur_c0 = pf_c0, cur_c1 = pf_c1, cur_c2 = pf_c2;
-            if (stage > 0) {
-                if (pf_has_y) pf_y = __ldcs(pf_yp + (size_t)(stage - 1) * D);
-                if (pf_has_c) {
-                    const double* sc = pf_cp + (size_t)(stage - 1) * P * 3;
-                    pf_c0 = __ldcs(sc); pf_c1 = __ldcs(sc + 1); pf_c2 = __ldcs(sc + 2);
-                }
-            }
             // stage adjoint kbar, stage input y
             for (int g = tid; g < W * D; g += T) {
                 int w = g / D, e = g - w * D;
@@ -122,7 +102,7 @@ __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
                 kb(w)[e] = k;
                 if (b < a.B) {
                     a.kbar[(b * NS + stage) * D + e] = k;
-                    yy(w)[e] = g == tid ? cur_y : a.stash_y[(b * NS + stage) * D + e];
+                    yy(w)[e] = a.stash_y[(b * NS + stage) * D + e];
                 } else {
                     yy(w)[e] = (double)(e >> 1) + 0.37 * (e & 1);
                 }
@@ -132,7 +112,10 @@ __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
                 long long b = base + it_w;
                 double f0 = 0, f1 = 0, f2 = 0, kd = 0;
                 if (b < a.B) {
-                    if (!RECOMPUTE) { f0 = cur_c0; f1 = cur_c1; f2 = cur_c2; }
+                    if (!RECOMPUTE) {
+                        const double* sc = a.stash_c + ((b * NS + stage) * P + it_p) * 3;
+                        f0 = sc[0]; f1 = sc[1]; f2 = sc[2];
+                    }
                     kd = a.gbar_delta[b] * h * ((sub == 0 || sub == 3) ? 0.125 : 0.375);
                 }
                 const double* y = yy(it_w);
@@ -180,6 +163,111 @@ __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
                 if (b < a.B) a.grad_x[b * D + e] = ubar(w)[e];
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// The same reverse sweep with ONE WARP PER WALKER: no CTA-wide barrier (three __syncwarp per stage), every warp
+// of the SM an independent walker.  Items p = lane, lane + 32, ...; the arithmetic and the order of every sum are
+// those of adjoint_kernel, so the two kernels agree bit for bit.  The pair sums walk the pair index
+// incrementally instead of recomputing pair_index() per term.
+// Shared memory: the (i, j) byte tables once per CTA, then per warp ubar[D], kb[D], in4/in3/in2[D], y[D], vec[P][2].
+// ---------------------------------------------------------------------------------------
+__host__ __device__ inline int adjoint_warp_slice(int D, int P) { return 6 * D + 2 * P; }
+
+template <bool RECOMPUTE>
+__global__ void __launch_bounds__(256, 4) adjoint_warp_kernel(const AdjArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    const int n = a.n, D = a.D, P = a.P, NP = a.NP;
+    const int NS = 4 * a.nsteps;
+    const bool has_mu = a.H_mu > 0;
+    unsigned char* pair_i = reinterpret_cast<unsigned char*>(smem);
+    unsigned char* pair_j = pair_i + ((NP + 7) & ~7);
+    double* wb = smem + 2 * ((NP + 7) / 8) + (size_t)warp * adjoint_warp_slice(D, P);
+    double* ubar = wb;
+    double* kb = wb + D;
+    double* yy = wb + 5 * D;
+    double* vec = wb + 6 * D;
+    auto ib = [&](int s) { return wb + (2 + s) * D; };                 // s = 0,1,2 <-> in4,in3,in2 bars
+    for (int p = tid; p < NP; p += T) {
+        int i = 0, rem = p;
+        while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+        pair_i[p] = (unsigned char)i;
+        pair_j[p] = (unsigned char)(i + 1 + rem);
+    }
+    __syncthreads();
+    const double h = a.h;
+    const RtHeader rt_e = rt_load_header(RECOMPUTE ? a.rt_eta : nullptr);
+    const RtHeader rt_m = rt_load_header(RECOMPUTE && has_mu ? a.rt_mu : nullptr);
+
+    for (long long b = (long long)blockIdx.x * nwarp + warp; b < a.B; b += (long long)gridDim.x * nwarp) {
+        for (int e = lane; e < D; e += 32) ubar[e] = a.gbar_z[b * D + e];
+        const double gd = a.gbar_delta[b];
+        __syncwarp();
+        for (int stage = NS - 1; stage >= 0; --stage) {
+            const int sub = stage & 3;
+            for (int e = lane; e < D; e += 32) {                         // stage adjoint kbar, stage input y
+                const double u = ubar[e];
+                double k;
+                if (sub == 3) k = 0.125 * h * u;
+                else if (sub == 2) k = 0.375 * h * u + h * ib(0)[e];
+                else if (sub == 1) k = 0.375 * h * u + h * (ib(1)[e] - ib(0)[e]);
+                else k = 0.125 * h * u + h * (ib(0)[e] + (ib(2)[e] - ib(1)[e]) * (1.0 / 3.0));
+                kb[e] = k;
+                a.kbar[(b * NS + stage) * D + e] = k;
+                yy[e] = a.stash_y[(b * NS + stage) * D + e];
+            }
+            __syncwarp();
+            const double kd = gd * h * ((sub == 0 || sub == 3) ? 0.125 : 0.375);
+            for (int p = lane; p < P; p += 32) {
+                const bool is_pair = p < NP;
+                double f0 = 0, f1 = 0, f2 = 0;
+                if (!RECOMPUTE) {
+                    const double* sc = a.stash_c + ((b * NS + stage) * P + p) * 3;
+                    f0 = sc[0]; f1 = sc[1]; f2 = sc[2];
+                }
+                double rx, ry, kx, ky;
+                if (is_pair) {
+                    const int i = pair_i[p], j = pair_j[p];
+                    rx = yy[2 * i] - yy[2 * j]; ry = yy[2 * i + 1] - yy[2 * j + 1];
+                    kx = kb[2 * i] - kb[2 * j]; ky = kb[2 * i + 1] - kb[2 * j + 1];
+                } else {
+                    const int i = p - NP;
+                    rx = yy[2 * i]; ry = yy[2 * i + 1]; kx = kb[2 * i]; ky = kb[2 * i + 1];
+                }
+                const double d = sqrt(fma(rx, rx, ry * ry));
+                if (RECOMPUTE) {
+                    double f[4];
+                    if (!radial_table_eval<2>(is_pair ? rt_e : rt_m, d, f)) {
+                        if (is_pair) radial_direct_global(a.eta_w1, a.eta_b1, a.eta_w2, a.H_eta, d, f);
+                        else radial_direct_global(a.mu_w1, a.mu_b1, a.mu_w2, a.H_mu, d, f);
+                    }
+                    f0 = f[0]; f1 = f[1]; f2 = f[2];
+                }
+                const double alpha = fma(kx, rx, ky * ry);
+                const double q1 = (is_pair ? 2.0 : 1.0) * fma(f2, d, 3.0 * f1);
+                const double c = (alpha * f1 - kd * q1) / d;
+                vec[2 * p] = fma(kx, f0, c * rx);
+                vec[2 * p + 1] = fma(ky, f0, c * ry);
+            }
+            __syncwarp();
+            for (int e = lane; e < D; e += 32) {
+                const int i = e >> 1, c = e & 1;
+                double acc = 0.0;
+                int idx = i - 1;                                          // pair_index(0, i)
+                for (int j = 0; j < i; ++j) { acc -= vec[2 * idx + c]; idx += n - 2 - j; }
+                const double* vr = vec + 2 * pair_index(i, i + 1, n) + c;
+                for (int j = i + 1; j < n; ++j) { acc += *vr; vr += 2; }
+                if (has_mu) acc += vec[2 * (NP + i) + c];
+                if (sub > 0) ib(3 - sub)[e] = acc;
+                else ubar[e] += acc + ib(0)[e] + ib(1)[e] + ib(2)[e];
+            }
+            __syncwarp();
+        }
+        if (a.grad_x)
+            for (int e = lane; e < D; e += 32) a.grad_x[b * D + e] = ubar[e];
+        __syncwarp();
     }
 }
 

@@ -648,3 +648,38 @@ def test_backward_with_and_without_radial_stash(dev, case):
     for a, b in zip(got, ref):
         assert torch.isfinite(a).all()
         close(a, b, 1e-11, 1e-13 * float(max(r.abs().max() for r in ref)))
+
+
+@pytest.mark.parametrize("nup,ndn,Hm,stash_c", [(10, 10, 16, True), (10, 10, 16, False), (3, 2, 0, True), (6, 6, 8, True)])
+def test_adjoint_warp_kernel_matches_cta_kernel(dev, nup, ndn, Hm, stash_c):
+    """The one-warp-per-walker reverse sweep (default) performs the arithmetic of the CTA-synchronous kernel
+    (FF_ADJ_CTA=1) in the same order: d log p / dx is bit-identical, with and without the (f, f', f'') stash."""
+    from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
+    gen = torch.Generator().manual_seed(17)
+    H = 16
+    mlps = [MLP(1, H)] + ([MLP(1, Hm)] if Hm else [])
+    with torch.no_grad():
+        for m in mlps:
+            m.fc1.weight.copy_(torch.randn(m.fc1.weight.shape, generator=gen))
+            m.fc1.bias.copy_(torch.randn(m.fc1.bias.shape, generator=gen))
+            m.fc2.weight.copy_(2e-2 * torch.randn(m.fc2.weight.shape, generator=gen))
+    v = Backflow(mlps[0].to(dev), mu=mlps[1].to(dev)) if Hm else Backflow(mlps[0].to(dev))
+    model = GSVMC(nup, ndn, HO2D(), FreeFermion(dev), CNF(v, (0.0, 1.0), nsteps=5), CoulombPairPotential(2.0),
+                  sp_potential=HO()).to(dev)
+    B = 1037                                       # not a multiple of the warps per CTA
+    x = model.cnf.generate(model.basedist.sample(model.orbitals_up, model.orbitals_down, (B,)))
+    w = torch.randn(B, generator=gen).to(dev) / B
+
+    def grad_x():
+        for p in model.parameters():
+            p.grad = None
+        xr = x.clone().requires_grad_(True)
+        (model.logp(xr, params_require_grad=True) * w).sum().backward()
+        return xr.grad.clone()
+    env = {} if stash_c else dict(FF_NO_STASH_C="1")
+    with _env(FF_ADJ_CTA=None, **env):
+        g_warp = grad_x()
+    with _env(FF_ADJ_CTA="1", **env):
+        g_cta = grad_x()
+    assert torch.isfinite(g_warp).all()
+    assert torch.equal(g_warp, g_cta)
