@@ -178,8 +178,14 @@ int launch_flow_warp(ff::FlowArgs& a, cudaStream_t st) {
     const int warps = 8;
     int common = ff::kTabDoubles + 6 * (((a.H_eta + 3) & ~3) + ((a.H_mu + 3) & ~3));
     common = even(common) + 2 * ((a.NP + 7) / 8) + 2;
-    const size_t smem = (size_t)(common + (long long)warps * wg.slice) * 8;
+    size_t smem = (size_t)(common + (long long)warps * wg.slice) * 8;
     if (smem > (size_t)di.smem_optin) return 1;
+    {   // spare shared memory at FF_WARP_MINB CTAs per SM mirrors the head of the eta Taylor table
+        const long long room = (long long)di.smem_sm / FF_WARP_MINB - di.smem_reserved - (long long)smem - 64;
+        a.rt_cache_nodes = (a.rt_eta != nullptr && room > 0 && getenv("FF_NO_RT_CACHE") == nullptr)
+                               ? (int)std::min<long long>(room / (8 * ff::kRtCoef), 2048) : 0;
+        smem += (size_t)a.rt_cache_nodes * 8 * ff::kRtCoef;
+    }
     auto kernel = ff::flow_warp_kernel<MODE>;
     FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));

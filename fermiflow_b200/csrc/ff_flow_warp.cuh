@@ -93,6 +93,12 @@ __global__ void __launch_bounds__(256, FF_WARP_MINB) flow_warp_kernel(const Flow
         pair_i[p] = (unsigned char)i;
         pair_j[p] = (unsigned char)(i + 1 + rem);
     }
+    // Taylor tables: headers in registers, the first nodes of the eta table (short pair distances: most items)
+    // mirrored in shared memory behind the warp slices -- the look-up is otherwise an L2 round trip per item
+    const RtHeader rt_e = rt_load_header(a.rt_eta), rt_m = rt_load_header(a.rt_mu);
+    double* rt_cache = wb0 + (size_t)nwarp * wg.slice;
+    const int ncache = rt_e.coef != nullptr ? min(a.rt_cache_nodes, rt_e.n_nodes) : 0;
+    for (int e = tid; e < ncache * kRtCoef; e += blockDim.x) rt_cache[e] = rt_e.coef[e];
     __syncthreads();
 
     const double h = (a.tb - a.ta) / a.nsteps;
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(256, FF_WARP_MINB) flow_warp_kernel(const Flow
 #pragma unroll
                     for (int k = 0; k < NI; ++k) {
                         double g[4];
-                        const bool hk = radial_table_eval<ORD>(a.rt_eta, d[k], g);
+                        const bool hk = radial_table_eval_cached<ORD>(rt_e, rt_cache, ncache, d[k], g);
                         f[k][0] = g[0]; f[k][1] = g[1]; f[k][2] = g[2];
                         hit = hit && (hk || !ok[k]);
                     }
@@ -154,7 +160,7 @@ __global__ void __launch_bounds__(256, FF_WARP_MINB) flow_warp_kernel(const Flow
                     d[0] = sqrt(fma(rx[0], rx[0], ry[0] * ry[0]));
                     {
                         double g[4];
-                        const bool hit = radial_table_eval<ORD>(a.rt_mu, d[0], g) || !ok;
+                        const bool hit = radial_table_eval<ORD>(rt_m, d[0], g) || !ok;
                         f[0][0] = g[0]; f[0][1] = g[1]; f[0][2] = g[2];
                         if (__any_sync(0xffffffffu, !hit)) radial_mlp_items<ORD, 1>(coef_mu, a.H_mu, d, tabl, f);
                     }

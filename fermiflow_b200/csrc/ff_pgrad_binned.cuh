@@ -31,8 +31,11 @@ constexpr double kPgDmax = 24.0;         // node range of the pair distances (be
 constexpr double kPgDmaxMu = 12.0;       // node range of the distances from the trap centre
 constexpr double kPgMaxDelta = 0.25;
 constexpr int kPgHdr = 16;
-// work layout (doubles): hdr[kPgHdr] | mom[kPgMaxBins][2 kPgMom] | direct[3 (H_eta + H_mu)]
-__host__ __device__ inline size_t pgrad_binned_work_doubles(int Ht) { return kPgHdr + (size_t)kPgMaxBins * 2 * kPgMom + 3 * (size_t)Ht; }
+constexpr int kPgHist = 512;             // coarse histogram of sampled pair distances over [0, kPgDmax] (int counters)
+constexpr double kPgQuantile = 0.999;    // the eta nodes cover this fraction of the pair records; the tail is summed directly
+// work layout (doubles): hdr[kPgHdr] | mom[kPgMaxBins][2 kPgMom] | direct[3 (H_eta + H_mu)] | hist[kPgHist ints]
+__host__ __device__ inline size_t pgrad_binned_zeroed_doubles(int Ht) { return kPgHdr + (size_t)kPgMaxBins * 2 * kPgMom + 3 * (size_t)Ht; }
+__host__ __device__ inline size_t pgrad_binned_work_doubles(int Ht) { return pgrad_binned_zeroed_doubles(Ht) + kPgHist / 2; }
 
 struct PGradBinArgs {
     int n, H_eta, H_mu, nsteps;
@@ -45,12 +48,42 @@ struct PGradBinArgs {
     double *ge_w1, *ge_b1, *ge_w2, *gm_w1, *gm_b1, *gm_w2;
 };
 
-// hdr: [0] inv_delta_eta [1] delta_eta [2] bins_eta [3] inv_delta_mu [4] delta_mu [5] bins_mu [6] valid
+// Coarse histogram of the pair distances of every `stride`-th stage input (about 65 k rows): the setup kernel
+// places the eta nodes over [0, its 99.9 % quantile] instead of [0, kPgDmax], so that the populated bins are as
+// fine -- and the hottest bin of a tile as short -- as the 640 threads allow.
+__global__ void __launch_bounds__(256) pgrad_hist_kernel(const PGradBinArgs a, long long stride) {
+    __shared__ int hist[kPgHist];
+    __shared__ unsigned char pi[32768 / 2], pj[32768 / 2];
+    const int tid = threadIdx.x, n = a.n, D = a.D, NP = a.NP;
+    for (int k = tid; k < kPgHist; k += blockDim.x) hist[k] = 0;
+    for (int p = tid; p < NP; p += blockDim.x) {
+        int i = 0, rem = p;
+        while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+        pi[p] = (unsigned char)i; pj[p] = (unsigned char)(i + 1 + rem);
+    }
+    __syncthreads();
+    const long long nrec = a.B * 4LL * a.nsteps;
+    for (long long row = (long long)blockIdx.x * stride; row < nrec; row += (long long)gridDim.x * stride) {
+        const double* y = a.stash_y + row * D;
+        for (int p = tid; p < NP; p += blockDim.x) {
+            const int i = pi[p], j = pj[p];
+            const double rx = y[2 * i] - y[2 * j], ry = y[2 * i + 1] - y[2 * j + 1];
+            const double d = sqrt(fma(rx, rx, ry * ry));
+            const double kf = d * (kPgHist / kPgDmax);
+            atomicAdd(&hist[kf < (double)(kPgHist - 1) ? (int)kf : kPgHist - 1], 1);      // NaN -> last bin
+        }
+    }
+    __syncthreads();
+    int* gh = reinterpret_cast<int*>(a.work + pgrad_binned_zeroed_doubles(a.H_eta + a.H_mu));
+    for (int k = tid; k < kPgHist; k += blockDim.x) if (hist[k]) atomicAdd(gh + k, hist[k]);
+}
+
+// hdr: [0] inv_delta_eta [1] delta_eta [2] bins_eta [3] inv_delta_mu [4] delta_mu [5] bins_mu [6] valid [7] eta node range
 __global__ void __launch_bounds__(256) pgrad_bins_setup_kernel(const PGradBinArgs a) {
     __shared__ double red[256];
     const int Ht = a.H_eta + a.H_mu;
     double* hdr = a.work;
-    const size_t total = pgrad_binned_work_doubles(Ht);
+    const size_t total = pgrad_binned_zeroed_doubles(Ht);
     for (size_t i = kPgHdr + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) a.work[i] = 0.0;
     if (blockIdx.x != 0) return;
     double wmx[2];
@@ -72,13 +105,25 @@ __global__ void __launch_bounds__(256) pgrad_bins_setup_kernel(const PGradBinArg
         const double dm_max = fmin(kPgMaxDelta, kPgSpacing / fmax(wmx[1], 1e-300));
         const double de_max = fmin(kPgMaxDelta, kPgSpacing / fmax(wmx[0], 1e-300));
         const double nbm = a.H_mu > 0 ? ceil(kPgDmaxMu / dm_max) + 1.0 : 0.0;
-        const double nbe_min = ceil(kPgDmax / de_max) + 1.0;
+        // node range of eta: the kPgQuantile quantile of the sampled pair distances plus one histogram cell
+        double range = kPgDmax;
+        {
+            const int* gh = reinterpret_cast<const int*>(a.work + total);
+            long long all = 0, cum = 0;
+            for (int k = 0; k < kPgHist; ++k) all += gh[k];
+            if (all > 0) {
+                int q = 0;
+                for (; q < kPgHist; ++q) { cum += gh[q]; if ((double)cum >= kPgQuantile * (double)all) break; }
+                range = fmin(kPgDmax, fmax(1.0, (q + 2) * (kPgDmax / kPgHist)));
+            }
+        }
+        const double nbe_min = ceil(range / de_max) + 1.0;
         const bool ok = isfinite(wmx[0]) && isfinite(wmx[1]) && nbm + nbe_min <= (double)kPgMaxBins;
         const double nbe = ok ? (double)kPgMaxBins - nbm : nbe_min;
-        const double de = ok ? kPgDmax / (nbe - 1.0) : de_max;
+        const double de = ok ? range / (nbe - 1.0) : de_max;
         hdr[0] = 1.0 / de; hdr[1] = de; hdr[2] = nbe;
         hdr[3] = 1.0 / dm_max; hdr[4] = dm_max; hdr[5] = nbm;
-        hdr[6] = ok ? 1.0 : 0.0;
+        hdr[6] = ok ? 1.0 : 0.0; hdr[7] = range;
     }
 }
 
