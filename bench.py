@@ -252,7 +252,7 @@ def run_ours(args):
                    "parallelism": "walkers sharded, dp%d" % world},
         "e2e": {"value": total_walkers / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": nparam * 8, "d2h_bytes_per_step": (nparam + 2) * 8},
-        "gpu_launches": 14 * args.steps,   # metropolis, generate + 2 table kernels, eloc + 2 table kernels, slater, adjoint, 3 binned-gradient kernels, direct pgrad + finish (device-side early exit)
+        "gpu_launches": 15 * args.steps,   # metropolis, generate + 2 table kernels, eloc + 2 table kernels, slater, adjoint, distance histogram + 3 binned-gradient kernels, direct pgrad + finish (device-side early exit)
         "clocks": sampler.summary(),
         "breakdown_ms": {k: round(v, 2) for k, v in bd.items()},
         "roofline": {"bound": "fp64", "kernel": "ff::eloc2_kernel<20,1> (E_loc sweep)", "achieved": fl / (eloc_ms * 1e-3) / 1e12,
