@@ -264,9 +264,9 @@ def run_ours(args):
                                       else "reference formulation (every hidden unit evaluated)",
                      "reference_formulation": {"tflops_equivalent": fl_ref / (eloc_ms * 1e-3) / 1e12,
                                                "frac_equivalent": fl_ref / (eloc_ms * 1e-3) / peak.value},
-                     # ncu --set full (profiles/r01_eloc_ncu_full.md): 2.80 GB DRAM traffic for 8288 walkers
-                     "traffic": 2.80e9 / 8288 * B if (n == 20 and args.hidden == 50 and args.ode_steps == 16) else None,
-                     "traffic_source": "ncu dram__bytes_read+write, 8288-walker capture scaled per walker",
+                     # ncu --set full (profiles/r01_eloc_ncu_full.md): 3.211 GB written + 0.021 GB read for 9472 walkers
+                     "traffic": 3.2323e9 / 9472 * B if (n == 20 and args.hidden == 50 and args.ode_steps == 16) else None,
+                     "traffic_source": "ncu dram__bytes_read+write, 9472-walker capture scaled per walker",
                      "kernel_ms": eloc_ms,
                      "hbm": {"achieved": by / (eloc_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": by / (eloc_ms * 1e-3) / 1e9 / hbm_peak}},
