@@ -93,14 +93,51 @@ class CNF(torch.nn.Module):
         return self.v._model(n, self.t_span, self.nsteps, n_up=n_up)
 
     def generate(self, z, nframes=None):               # flow.py:42-50
-        if nframes is not None:
-            raise NotImplementedError("trajectory frames (nframes) are visualisation only and not on the CUDA path")
         z = z.detach().contiguous()
         B, n, _ = z.shape
+        if nframes is not None:
+            # trajectory at torch.linspace(*t_span, nframes) (flow.py:46-49): one fixed-grid sweep per segment,
+            # ceil(nsteps / (nframes - 1)) RK4 steps each; equals generate(z) at the last frame when
+            # nframes - 1 divides nsteps (same step size, same arithmetic)
+            nframes = int(nframes)
+            if nframes < 2:
+                raise ValueError("CNF.generate: nframes must be at least 2")
+            seg = -(-self.nsteps // (nframes - 1))
+            t0, t1 = self.t_span
+            ts = [t0 + (t1 - t0) * k / (nframes - 1) for k in range(nframes)]
+            ts[-1] = t1
+            frames = torch.empty(nframes, *z.shape, dtype=z.dtype, device=z.device)
+            frames[0] = z
+            for k in range(1, nframes):
+                m = self.v._model(n, (ts[k - 1], ts[k]), seg)
+                L.check(L.lib().ff_cnf_generate(C.byref(m), L.ptr(frames[k - 1]), B, 0, L.ptr(frames[k]), L.stream()))
+            return frames
         m = self._model(n)
         x = torch.empty_like(z)
         L.check(L.lib().ff_cnf_generate(C.byref(m), L.ptr(z), B, 0, L.ptr(x), L.stream()))
         return x
+
+    def check_reversibility(self, basedist, batch, orbitals_up=None, orbitals_down=()):   # flow.py:58-71
+        """z -> x with log p carried along, then x -> z: prints and returns the two maximal deviations.
+        basedist.sample / log_prob take the orbitals when given (FreeFermion), else the reference's signature."""
+        print("---- CNF REVERSIBILITY CHECK ----")
+        if orbitals_up is not None:
+            z = basedist.sample(orbitals_up, orbitals_down, (batch,))
+            logp0 = lambda y: basedist.log_prob(orbitals_up, orbitals_down, y)
+        else:
+            z = basedist.sample((batch,))
+            logp0 = basedist.log_prob
+        x = self.generate(z)
+        # forward-time integral of -div v: the same sweep on the reversed interval
+        fwd = CNF(self.v, (self.t_span[1], self.t_span[0]), nsteps=self.nsteps)
+        x2, dl_fwd = fwd.delta_logp(z)
+        logp = logp0(z) + dl_fwd
+        z_reverse, delta_logp = self.delta_logp(x)
+        logp_reverse = logp0(z_reverse) - delta_logp
+        dz, dlp = (z_reverse - z).abs().max(), (logp_reverse - logp).abs().max()
+        print("MaxAbs of z_reverse - z:", dz)
+        print("MaxAbs of logp_inverse - logp:", dlp)
+        return float(dz), float(dlp), float((x2 - x).abs().max())
 
     def delta_logp(self, x, params_require_grad=False):  # flow.py:52-56
         params = _flat_params(self.v) if params_require_grad else []

@@ -683,3 +683,27 @@ def test_adjoint_warp_kernel_matches_cta_kernel(dev, nup, ndn, Hm, stash_c):
         g_cta = grad_x()
     assert torch.isfinite(g_warp).all()
     assert torch.equal(g_warp, g_cta)
+
+
+def test_generate_trajectory_frames_and_reversibility_check(dev, O):
+    """CNF.generate(z, nframes) (flow.py:46-49): frame k is the flow to t_k = linspace(t0, t1, nframes)[k]; checked
+    against the oracle's fixed-grid flow over [t0, t_k], and bit-identical to generate(z) at the last frame when
+    nframes - 1 divides nsteps.  CNF.check_reversibility (flow.py:58-71) closes within the RK4 error."""
+    from fermiflow_b200 import Backflow, CNF, HO2D, FreeFermion
+    eta, mu = rand_mlp(12, 3, 0.05, dev), rand_mlp(9, 4, 0.05, dev)
+    cnf = CNF(Backflow(eta, mu=mu), (0.0, 1.5), nsteps=12)
+    z = 0.9 * torch.randn(37, 6, 2, generator=torch.Generator().manual_seed(2)).to(dev)
+    frames = cnf.generate(z, nframes=5)
+    assert frames.shape == (5, 37, 6, 2)
+    assert torch.equal(frames[0], z)
+    assert torch.equal(frames[-1], cnf.generate(z))
+    pe, pm = cpu_params(eta), cpu_params(mu)
+    for k in (1, 2, 3, 4):
+        ref = O.cnf_generate(z.cpu(), pe, pm, (0.0, 1.5 * k / 4), 3 * k)
+        close(frames[k], ref, 1e-12)
+    frames7 = cnf.generate(z, nframes=8)          # 7 segments of ceil(12 / 7) = 2 steps
+    close(frames7[-1], O.cnf_generate(z.cpu(), pe, pm, (0.0, 1.5), 14), 1e-12)
+    ho = HO2D()
+    cnf32 = CNF(Backflow(eta, mu=mu), (0.0, 1.0), nsteps=32)
+    dz, dlp, dx = cnf32.check_reversibility(FreeFermion(dev), 256, ho.orbitals[:3], ho.orbitals[:3])
+    assert dz < 1e-6 and dlp < 1e-5 and dx < 1e-12
