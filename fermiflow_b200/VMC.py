@@ -195,7 +195,10 @@ class BetaVMC(_VMCBase):
         self.logp_states_all = logp_all.detach()
         self.S_analytical = -(self.logp_states_all * self.logp_states_all.exp()).sum().item()
 
-        gradF_phi = (logp_states * (Floc - self.F)).sum() / nglobal
+        # sum_w logp_all[state_w] (Floc_w - F) = sum_s logp_all[s] * (sum of the weights of the walkers in s): the
+        # per-state sums are one index_add_, and autograd never sees an 8000-fold duplicated gather (VMC.py:159)
+        wstate = torch.zeros(self.Nstates, dtype=Eloc.dtype, device=Eloc.device).index_add_(0, state.long(), Floc - self.F)
+        gradF_phi = (logp_all * wstate).sum() / nglobal
 
         # E_loc minus its mean over the walkers that share a state (VMC.py:163-168)
         sl = state.long()

@@ -163,6 +163,14 @@ int launch_flow_kernel(K kernel, ff::FlowArgs& a, int threads, size_t smem, cuda
     if (occ < 1) return fail(-2, "flow kernel does not fit on an SM (threads %d, smem %zu)", threads, smem);
     long long nb = (a.B + a.W - 1) / a.W;
     long long grid = (long long)di.sms * occ;
+    if (a.W > 1 && a.B > 0 && getenv("FF_NO_W_BALANCE") == nullptr) {
+        // several walkers per CTA (small n): spread them evenly over the rounds the resident CTAs need anyway --
+        // 8000 walkers at W = 26 are 308 tasks for 296 CTAs (two rounds, the second almost empty); W = 14 gives 572
+        // tasks, two full rounds of half the length.  threads / smem were sized for the larger W and stay valid.
+        const long long rounds = (nb + grid - 1) / grid;
+        const long long Wb = (a.B + rounds * grid - 1) / (rounds * grid);
+        if (Wb < a.W) { a.W = (int)std::max<long long>(1, Wb); nb = (a.B + a.W - 1) / a.W; }
+    }
     if (grid > nb) grid = nb;
     if (grid < 1) return 0;
     kernel<<<(unsigned)grid, threads, smem, st>>>(a);

@@ -481,11 +481,10 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
                 }
             }
             if (MODE >= MODE_STASH && a.stash_y != nullptr) {
-                for (int w = 0; w < W; ++w) {
+                for (int q = tid; q < W * D; q += T) {              // flat over (walker, element): small n keeps every lane busy
+                    const int w = kS ? 0 : q / D, e = q - w * D;
                     const long long b = base + w;
-                    if (b < a.B)
-                        for (int e = tid; e < D; e += T)
-                            a.stash_y[(b * NS + stage) * D + e] = (wbase + (size_t)w * wstride)[e];
+                    if (b < a.B) a.stash_y[(b * NS + stage) * D + e] = (wbase + (size_t)w * wstride)[e];
                 }
             }
             FF_TICK(1);
@@ -521,10 +520,12 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
             {
                 constexpr int GRg = (MODE == MODE_ELOC) ? kGRec : 3;      // record stride
                 constexpr int NC = (MODE == MODE_ELOC) ? kGRec : (MODE >= MODE_DIV ? 3 : 2);
-                for (int w = 0; w < W; ++w) {
+                for (int gg = tid; gg < W * n * NC; gg += T) {           // flat over (walker, particle, quantity)
+                    const int w = kS ? 0 : gg / (n * NC);
+                    const int g = gg - w * (n * NC);
                     double* Sw = wbase + (size_t)w * wstride;
                     const double* G = Sw + off_G;
-                    for (int g = tid; g < n * NC; g += T) {
+                    {
                         const int i = g / NC, cc = g - i * NC;
                         const int c = (MODE == MODE_ELOC) ? cc : (cc == 2 ? 6 : cc);   // logical quantity
                         const int gc = cc;                                             // column in the record
@@ -678,8 +679,7 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
             __syncthreads();
             FF_TICK(10);
             // ======== S4: 3/8-rule RK4 bookkeeping (torchdiffeq rk4_alt_step_func) ========
-            for (int w = 0; w < W; ++w) {
-                double* Sw = wbase + (size_t)w * wstride;
+            {
                 // element e of the state block <-> element pe of the partial / derivative blocks
                 auto upd = [&](double* s, double* p3, double* p4, double* po, const double* kk) {
                     const double k = *kk * h;
@@ -695,14 +695,16 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
                         *s = fma(k, 0.125, *po);
                     }
                 };
-                for (int e = tid; e < NV; e += T) upd(Sw + e, Sw + oP3 + e, Sw + oP4 + e, Sw + oPO + e, Sw + oK + e);
+                // flat over (walker, element): with many small walkers per CTA every lane stays busy
+                for (int q = tid; q < W * NV; q += T) {
+                    const int w = kS ? 0 : q / NV, e = q - w * NV;
+                    double* Sw = wbase + (size_t)w * wstride;
+                    upd(Sw + e, Sw + oP3 + e, Sw + oP4 + e, Sw + oPO + e, Sw + oK + e);
+                }
                 if (MODE == MODE_ELOC) {
-                    // J: state rows have stride DP, partial rows stride D; one row per warp trip,
-                    // two columns per lane (no integer division in the loop)
+                    // J: state rows have stride DP, partial rows stride D
                     const int hD = D >> 1;
-                    for (int r = warp; r < D; r += nwarp)
-                    for (int c2 = lane; c2 < hD; c2 += 32) {
-                        const int c = 2 * c2;
+                    auto updJ = [&](double* Sw, int r, int c) {
                         double2* s2 = reinterpret_cast<double2*>(Sw + NV + r * DP + c);
                         const int pe = NV + r * D + c;
                         double2* p3 = reinterpret_cast<double2*>(Sw + oP3 + pe);
@@ -728,6 +730,22 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
                         } else {
                             const double2 ao = *po;
                             *s2 = make_double2(fma(k.x, 0.125, ao.x), fma(k.y, 0.125, ao.y));
+                        }
+                    };
+                    if (kS || hD >= 16) {
+                        // one (walker, row) per warp trip, two columns per lane (no integer division in the inner loop)
+                        for (int wr = warp; wr < W * D; wr += nwarp) {
+                            const int w = kS ? 0 : wr / D, r = wr - w * D;
+                            double* Sw = wbase + (size_t)w * wstride;
+                            for (int c2 = lane; c2 < hD; c2 += 32) updJ(Sw, r, 2 * c2);
+                        }
+                    } else {
+                        // short rows (small n, many walkers per CTA): flat over (walker, row, column pair)
+                        const int per = D * hD;
+                        for (int q = tid; q < W * per; q += T) {
+                            const int w = q / per, rc = q - w * per;
+                            const int r = rc / hD, c2 = rc - r * hD;
+                            updJ(wbase + (size_t)w * wstride, r, 2 * c2);
                         }
                     }
                 }
