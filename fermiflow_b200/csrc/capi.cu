@@ -266,7 +266,8 @@ int launch_eloc2(ff::FlowArgs& a, cudaStream_t st) {
     a.off_G = g.off_G; a.off_AM = g.off_AM; a.off_u = g.off_u; a.off_kLx = g.off_kLx; a.off_part = g.off_part;
     a.off_x0 = g.off_x0; a.off_sl = g.off_sl; a.wstride = g.wstride; a.W = 1;
     const int need = ff::slater_scratch_size(a.n_up, a.n - a.n_up) + 2 * g.D + g.n * g.n + g.NP + 8;
-    if (need > 2 * g.MAT) return 1;            // e.g. all particles in one spin block: the generic kernel takes over
+    // finale scratch: the two RK partial buffers plus J1 (dead after the last stage; eloc2_kernel re-zeroes it)
+    if (need > 3 * g.MAT) return 1;            // the generic kernel takes over
     constexpr int NI = FF_ELOC2_ILP;
     const int common = ff::kTabDoubles + 6 * (ff::coef_rows2<NI>(a.H_eta) + ff::coef_rows2<NI>(a.H_mu)) + 2 * ((g.NP + 7) / 8) + 2;
     size_t smem = (size_t)(common + g.wstride) * 8;

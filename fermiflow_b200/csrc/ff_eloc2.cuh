@@ -640,6 +640,12 @@ eloc2_kernel(const FlowArgs a) {
         if (a.y_out) for (int e = tid; e < D; e += NT) a.y_out[b * D + e] = S[e];
         if (a.delta_out && tid == 0) a.delta_out[b] = S[G_.oS];
         eloc_finale(a, b, S, pair_i, pair_j);
+        // a large spin block (e.g. all particles polarised) lets the finale scratch run past the two RK partial
+        // buffers into J1, which is dead by then (the final J is in J0): restore its zero padding for the next walker
+        if (slater_scratch_size(a.n_up, n - a.n_up) + 2 * D + n * n + NP + 8 > 2 * MAT) {
+            __syncthreads();
+            for (int e = tid; e < MAT; e += NT) S[G_.oJ1 + e] = 0.0;
+        }
     }
 }
 

@@ -185,6 +185,7 @@ CASES = [  # nup, ndown, H_eta, H_mu, nsteps, batch
     (3, 0, 8, 0, 8, 7),
     (1, 1, 5, 5, 4, 3),
     (6, 6, 16, 16, 8, 9),
+    (12, 0, 10, 10, 4, 6),      # spin-polarised N = 12 (BASELINE config 3): finale scratch extends into J1
     (5, 2, 50, 50, 4, 4),
 ]
 
@@ -707,3 +708,20 @@ def test_generate_trajectory_frames_and_reversibility_check(dev, O):
     cnf32 = CNF(Backflow(eta, mu=mu), (0.0, 1.0), nsteps=32)
     dz, dlp, dx = cnf32.check_reversibility(FreeFermion(dev), 256, ho.orbitals[:3], ho.orbitals[:3])
     assert dz < 1e-6 and dlp < 1e-5 and dx < 1e-12
+
+
+def test_eloc_static_kernel_spin_polarised_many_walkers_per_cta(dev):
+    """Spin-polarised N = 12 (BASELINE config 3): the statically specialised sweep keeps its finale scratch partly
+    in the dead J1 buffer and re-zeroes it; with ~7 walkers per CTA it must agree with the generic kernel
+    (FF_ELOC_V1=1 FF_NO_STATIC=1), walker by walker."""
+    from fermiflow_b200 import Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
+    cnf = CNF(Backflow(rand_mlp(20, 5, 0.03, dev), mu=rand_mlp(20, 6, 0.03, dev)), (0.0, 1.0), nsteps=3)
+    model = GSVMC(12, 0, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(8.0), sp_potential=HO()).to(dev)
+    _, x = model.sample((2101,))
+    with _env(FF_ELOC_V1=None, FF_NO_STATIC=None):
+        r0 = model.local_energy(x, stash=True)
+    with _env(FF_ELOC_V1="1", FF_NO_STATIC="1"):
+        r1 = model.local_energy(x, stash=True)
+    for k in ("z", "logp", "grad", "lap", "kinetic", "potential", "eloc"):
+        close(getattr(r1, k), getattr(r0, k), 1e-10, 1e-11)
+    close(r1.stash.y, r0.stash.y, 1e-13)
