@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(256) pgrad_bins_setup_kernel(const PGradBinArg
         const double nbm = a.H_mu > 0 ? ceil(kPgDmaxMu / dm_max) + 1.0 : 0.0;
         // node range of eta: the kPgQuantile quantile of the sampled pair distances plus one histogram cell
         double range = kPgDmax;
+        bool far = false;          // more than the tail fraction beyond kPgDmax (e.g. a flow that blew the dot up): the
+                                   // in-kernel direct sums would serialise the CTAs, pgrad_kernel does them in parallel
         {
             const int* gh = reinterpret_cast<const int*>(a.work + total);
             long long all = 0, cum = 0;
@@ -115,10 +117,11 @@ __global__ void __launch_bounds__(256) pgrad_bins_setup_kernel(const PGradBinArg
                 int q = 0;
                 for (; q < kPgHist; ++q) { cum += gh[q]; if ((double)cum >= kPgQuantile * (double)all) break; }
                 range = fmin(kPgDmax, fmax(1.0, (q + 2) * (kPgDmax / kPgHist)));
+                far = (double)gh[kPgHist - 1] > 4.0 * (1.0 - kPgQuantile) * (double)all;
             }
         }
         const double nbe_min = ceil(range / de_max) + 1.0;
-        const bool ok = isfinite(wmx[0]) && isfinite(wmx[1]) && nbm + nbe_min <= (double)kPgMaxBins;
+        const bool ok = !far && isfinite(wmx[0]) && isfinite(wmx[1]) && nbm + nbe_min <= (double)kPgMaxBins;
         const double nbe = ok ? (double)kPgMaxBins - nbm : nbe_min;
         const double de = ok ? range / (nbe - 1.0) : de_max;
         hdr[0] = 1.0 / de; hdr[1] = de; hdr[2] = nbe;

@@ -570,17 +570,19 @@ def test_radial_tables_match_direct_evaluation(dev, case):
     assert all(torch.isfinite(v).all() for v in got.values())
 
 
-@pytest.mark.parametrize("case", ["bench", "sharp", "too_sharp", "zero", "far", "no_mu"])
+@pytest.mark.parametrize("case", ["bench", "sharp", "too_sharp", "zero", "far", "far_few", "no_mu"])
 def test_binned_parameter_gradient_matches_direct(dev, case):
     """ff_logp_backward through binned Taylor moments (default) against the direct kernel that evaluates every
     hidden unit per record (FF_NO_BINNED_PGRAD=1).  sharp: max|w1| = 3 (bins just fit); too_sharp: max|w1| = 40,
-    the bins do not fit and the device-side flag hands the work to the direct kernel; far: records beyond the
-    node range take the in-kernel direct path; zero: all-zero MLPs; no_mu: no one-body function."""
+    the bins do not fit and the device-side flag hands the work to the direct kernel; far: 3.6 % of the pair records
+    beyond d = 24, more than the tail the in-kernel direct path is meant for -> the device-side flag selects the
+    direct kernel; far_few: 0.2 % beyond the node range, summed directly inside the binned kernel; zero: all-zero
+    MLPs; no_mu: no one-body function."""
     from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
     gen = torch.Generator().manual_seed(77)
     H = 20
     eta, mu = MLP(1, H), MLP(1, H)
-    scale = {"bench": 1.0, "sharp": 1.0, "too_sharp": 1.0, "zero": 0.0, "far": 1.0, "no_mu": 1.0}[case]
+    scale = {"zero": 0.0}.get(case, 1.0)
     with torch.no_grad():
         for m in (eta, mu):
             m.fc1.weight.copy_(scale * torch.randn(H, 1, generator=gen))
@@ -595,6 +597,8 @@ def test_binned_parameter_gradient_matches_direct(dev, case):
     z = model.basedist.sample(model.orbitals_up, model.orbitals_down, (257,))
     if case == "far":
         z = z.clone(); z[::5, 2, 1] -= 26.5
+    if case == "far_few":
+        z = z.clone(); z[::100, 2, 1] -= 26.5
     x = model.cnf.generate(z)
     w = torch.randn(257, generator=gen).to(dev) / 257
 
