@@ -212,7 +212,10 @@ int launch_flow(ff::FlowArgs& a, int threads, size_t smem, cudaStream_t st) {
     if constexpr (MODE != ff::MODE_ELOC) {
         // lane efficiency of the warp-per-walker layout: NP pair items over ceil(NP / 32) rounds
         const int rounds = (a.NP + 31) / 32;
-        if (a.NP > 0 && a.n <= 255 && 100 * a.NP >= 85 * 32 * rounds && getenv("FF_FLOW_CTA") == nullptr) {
+        // measured (scripts/dev_gen_time_n.py, 65536 walkers): N = 12 (66 pairs, 69 % of three rounds) 7.0 ms CTA-synchronous
+        // against 5.7 ms warp-per-walker; N = 9 (36 pairs, 56 %) 4.3 against 4.9 ms; N = 6 (15 pairs, 47 %) 2.0 against 3.8 ms
+        const int min_fill = getenv("FF_FLOW_WARP_FILL") ? atoi(getenv("FF_FLOW_WARP_FILL")) : 60;      // per cent of the lanes
+        if (a.NP > 0 && a.n <= 255 && 100 * a.NP >= min_fill * 32 * rounds && getenv("FF_FLOW_CTA") == nullptr) {
             const int r = launch_flow_warp<MODE>(a, st);
             if (r != 1) return r;
         }
