@@ -121,7 +121,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # its banner goes to stdout, before the JSON line
+        # NCCL's version banner (NCCL_DEBUG=VERSION, from the environment or an nccl.conf) goes to stdout, before
+        # the JSON line: keep warnings only unless the caller asked for more
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     from fermiflow_b200 import _lib as L
