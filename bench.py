@@ -121,9 +121,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's version banner (NCCL_DEBUG=VERSION, from the environment or an nccl.conf) goes to stdout, before
-        # the JSON line: keep warnings only unless the caller asked for more
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        # NCCL writes its version banner and debug lines (NCCL_DEBUG >= VERSION) to stdout by default, before the
+        # JSON line: send them to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":      # NCCL honours the file only above VERSION
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     from fermiflow_b200 import _lib as L
