@@ -98,7 +98,10 @@ __global__ void __launch_bounds__(256, FF_WARP_MINB) flow_warp_kernel(const Flow
     const RtHeader rt_e = rt_load_header(a.rt_eta), rt_m = rt_load_header(a.rt_mu);
     double* rt_cache = wb0 + (size_t)nwarp * wg.slice;
     const int ncache = rt_e.coef != nullptr ? min(a.rt_cache_nodes, rt_e.n_nodes) : 0;
-    for (int e = tid; e < ncache * kRtCoef; e += blockDim.x) rt_cache[e] = rt_e.coef[e];
+    for (int e = tid; e < ncache * kRtCoef; e += blockDim.x) {          // coefficient-major: cache[q][k]
+        const int k = e / kRtCoef, q = e - k * kRtCoef;
+        rt_cache[q * ncache + k] = rt_e.coef[e];
+    }
     __syncthreads();
 
     const double h = (a.tb - a.ta) / a.nsteps;
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(256, FF_WARP_MINB) flow_warp_kernel(const Flow
 #pragma unroll
                     for (int k = 0; k < NI; ++k) {
                         double g[4];
-                        const bool hk = radial_table_eval_cached<ORD>(rt_e, rt_cache, ncache, d[k], g);
+                        const bool hk = radial_table_eval_cached_t<ORD>(rt_e, rt_cache, ncache, d[k], g);
                         f[k][0] = g[0]; f[k][1] = g[1]; f[k][2] = g[2];
                         hit = hit && (hk || !ok[k]);
                     }

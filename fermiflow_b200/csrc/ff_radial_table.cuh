@@ -203,6 +203,35 @@ __device__ __forceinline__ bool radial_table_eval_cached(const RtHeader& T, cons
     f[0] = p0; f[1] = p1; f[2] = 2.0 * p2; f[3] = 6.0 * p3;
     return true;
 }
+// The same with a COEFFICIENT-MAJOR mirror (cache[q * ncache + k]): lanes that look up different nodes read
+// neighbouring words of one coefficient row instead of rows 96 bytes apart (4 bank groups) -- for kernels whose lanes
+// all look up at once (one warp per walker).
+template <int ORD>
+__device__ __forceinline__ bool radial_table_eval_cached_t(const RtHeader& T, const double* cache, int ncache, double d, double (&f)[4]) {
+    const double kf = rint(d * T.inv_delta);
+    if (T.coef == nullptr || !(kf < (double)T.n_nodes) || !(kf >= 0.0)) return false;
+    const double t = fma(-kf, T.delta, d);
+    const int k = (int)kf;
+    double c[kRtCoef];
+    if (k < ncache) {
+#pragma unroll
+        for (int q = 0; q < kRtCoef; ++q) c[q] = cache[q * ncache + k];
+    } else {
+        const double2* c2 = reinterpret_cast<const double2*>(T.coef + (size_t)k * kRtCoef);
+#pragma unroll
+        for (int q = 0; q < kRtCoef / 2; ++q) { const double2 v = __ldg(c2 + q); c[2 * q] = v.x; c[2 * q + 1] = v.y; }
+    }
+    double p0 = c[kRtDeg], p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+    for (int m = kRtDeg - 1; m >= 0; --m) {
+        if (ORD >= 3) p3 = fma(p3, t, p2);
+        if (ORD >= 2) p2 = fma(p2, t, p1);
+        if (ORD >= 1) p1 = fma(p1, t, p0);
+        p0 = fma(p0, t, c[m]);
+    }
+    f[0] = p0; f[1] = p1; f[2] = 2.0 * p2; f[3] = 6.0 * p3;
+    return true;
+}
 template <int ORD>
 __device__ __forceinline__ bool radial_table_eval(const double* __restrict__ T, double d, double (&f)[4]) {
     return radial_table_eval<ORD>(rt_load_header(T), d, f);
