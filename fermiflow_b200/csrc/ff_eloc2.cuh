@@ -498,7 +498,10 @@ eloc2_kernel(const FlowArgs a) {
     {
         const RtHeader he = rt_load_header(a.rt_eta);
         if (he.coef != nullptr) ncache = min(a.rt_cache_nodes, he.n_nodes);
-        for (int e = tid; e < ncache * kRtCoef; e += NT) rt_cache[e] = he.coef[e];
+        for (int e = tid; e < ncache * kRtCoef; e += NT) {            // coefficient-major: cache[q][k] (bank conflicts)
+            const int k = e / kRtCoef, q = e - k * kRtCoef;
+            rt_cache[q * ncache + k] = he.coef[e];
+        }
     }
     __syncthreads();
 
@@ -554,7 +557,7 @@ eloc2_kernel(const FlowArgs a) {
                 const double d = d2 * inv_d;
                 double f[4];
                 FF_TICK2(1);
-                const bool hit = radial_table_eval_cached<3>(my_rt, rt_cache, it_pair ? ncache : 0, d, f);
+                const bool hit = radial_table_eval_cached_t<3>(my_rt, rt_cache, it_pair ? ncache : 0, d, f);
                 if (__any_sync(0xffffffffu, !hit)) {            // rare: outside the table -> direct sums (whole warp)
                     double g[4];
                     radial_mlp_n<3, NI>(it_pair ? coef_eta : coef_mu, it_pair ? a.H_eta : a.H_mu, d, tabl, g);
