@@ -79,15 +79,42 @@ class _DeltaLogp(torch.autograd.Function):
         return (None, gx, None, *gparams)
 
 
+class _VHolder(torch.nn.Module):
+    """Parameter container with the reference's sub-module names (flow.py:18-37 `V_wrapper`, `F`): the kernels
+    read the MLP parameters directly, so these modules only exist to give state_dict() the reference's keys."""
+
+    def __init__(self, v):
+        super().__init__()
+        self.v = v
+
+
 class CNF(torch.nn.Module):
     """CNF(v, t_span, nsteps): v is a Backflow; nsteps RK4 steps across t_span
-    (the reference's adaptive dopri5 with rtol 1e-6 is replaced by a fixed grid)."""
+    (the reference's adaptive dopri5 with rtol 1e-6 is replaced by a fixed grid).
+
+    The backflow is registered as `v_wrapper.v` and `f.v` like the reference's CNF (flow.py:28, 37), so
+    state_dict() carries the reference's keys (`v_wrapper.v.eta.fc1.weight`, `f.v.eta.fc1.weight`, ...) and its
+    checkpoints load with strict=True; `cnf.v` is the same object.  Checkpoints written by round-1 builds of this
+    package (`v.eta...` keys) are remapped on load."""
 
     def __init__(self, v, t_span, nsteps=16):
         super().__init__()
-        self.v = v
+        self.v_wrapper = _VHolder(v)
+        self.f = _VHolder(v)
         self.t_span = (float(t_span[0]), float(t_span[1]))
         self.nsteps = int(nsteps)
+
+    @property
+    def v(self):
+        return self.v_wrapper.v
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        old = prefix + "v."
+        for k in [k for k in state_dict if k.startswith(old)]:
+            val = state_dict.pop(k)
+            for new in ("v_wrapper.v.", "f.v."):
+                state_dict.setdefault(prefix + new + k[len(old):], val)
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     def _model(self, n, n_up=None):
         return self.v._model(n, self.t_span, self.nsteps, n_up=n_up)

@@ -299,6 +299,29 @@ def categorical_from_uniforms(logits, u):
     return torch.sort(idx)[0]
 
 
+def beta_vmc_estimators(Eloc, state_idx, log_state_weights, beta):
+    """VMC.py:139-171 given the local energies: state_idx (batch,) sorted state index per walker
+    (VMC.py:97, 144-145), log_state_weights the (Nstates,) logits (a leaf tensor if its gradient is wanted).
+    Returns E, E_std, F, F_std, S, S_analytical, gradF_phi (scalar with graph, VMC.py:162) and theta_weights,
+    the per-walker factors of logp_full in gradF_theta (VMC.py:164-169: (Eloc - mean of Eloc over the walkers
+    of the same state) / batch)."""
+    Eloc = Eloc.detach()
+    logp_all = torch.log_softmax(log_state_weights, -1)          # Categorical(logits).log_prob
+    logp_states = logp_all[state_idx]
+    Floc = Eloc + logp_states.detach() / beta
+    F = Floc.mean().item()
+    out = dict(E=Eloc.mean().item(), E_std=Eloc.std().item(), F=F, F_std=Floc.std().item(),
+               S=-logp_states.detach().mean().item(),
+               S_analytical=-(logp_all.detach() * logp_all.detach().exp()).sum().item())
+    out["gradF_phi"] = (logp_states * (Floc - F)).mean()
+    x_mean = torch.empty_like(Eloc)
+    for s in torch.unique(state_idx):
+        sel = state_idx == s
+        x_mean[sel] = Eloc[sel].mean()
+    out["theta_weights"] = (Eloc - x_mean) / Eloc.shape[0]
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # Philox4x32-10 counter RNG (the generator the CUDA sampler uses), in numpy
 # --------------------------------------------------------------------------------------

@@ -180,5 +180,61 @@ def main():
     print("golden fixtures written to", os.path.normpath(OUT))
 
 
+def main_n20():
+    """The headline configuration (BASELINE.json configs[2]: N = 20, 10 up / 10 down, Deta = Dmu = 50) on the REAL
+    reference: `python oracle/gen_golden.py n20` -> tests/golden/pipeline_n20.npz.
+      * rk4s16_*: odeint(method="rk4", 16 steps) -- the discrete algorithm the CUDA sweeps implement: x, z, delta_logp,
+        log p to rounding; the reference's continuous-adjoint gradient / nested-adjoint Laplacian / E_loc on the same
+        grid (they differ from the exact discrete derivative at the O(h^4) level of the integrator);
+      * tight_*: the reference's adaptive dopri5 at rtol 1e-9 (gradient, Laplacian, E_loc, parameter gradients)."""
+    import time
+    os.makedirs(OUT, exist_ok=True)
+    ho2d = HO2D()
+    g = torch.Generator().manual_seed(20241017)
+    nup, ndown, batch, Z = 10, 10, 2, 2.0
+    eta, mu = make_mlp(50, 21, 0.02), make_mlp(50, 22, 0.02)
+    t_span = (0.0, 1.0)
+    cnf = CNF(Backflow(eta, mu=mu), t_span)
+    model = GSVMC(nup, ndown, ho2d, FreeFermion(), cnf, CoulombPairPotential(Z), sp_potential=HO())
+    # walkers of |Psi_0|^2 (the reference's own Metropolis sampler, base_dist.py:58) rather than Gaussian points:
+    # E_loc of the benchmark's magnitude, no accidental near-node configurations
+    torch.manual_seed(20241017)
+    zs = quiet(FreeFermion().sample, ho2d.orbitals[:nup], ho2d.orbitals[:ndown], (batch,))
+    wts = torch.randn(batch, generator=g) / batch
+    d = dict(nup=nup, ndown=ndown, Z=Z, t_span=np.array(t_span), z0=np_(zs), weights=np_(wts))
+    d.update(mlp_arrays(eta, "eta")); d.update(mlp_arrays(mu, "mu"))
+
+    def run(tag):
+        t0 = time.time()
+        xg = quiet(cnf.generate, zs)
+        xr = xg.detach().clone().requires_grad_(True)
+        z_back, dl = quiet(cnf.delta_logp, xr)
+        lp, gl, ll = quiet(y_grad_laplacian, model.logp, xr)
+        kin = -0.25 * ll - 0.125 * (gl ** 2).sum(dim=(-2, -1))
+        pot = model.pair_potential.V(xr) + model.sp_potential.V(xr)
+        for p in model.parameters():
+            p.grad = None
+        lp_full = quiet(model.logp, xr.detach(), params_require_grad=True)
+        quiet((lp_full * wts).sum().backward)
+        d.update({tag + "_x": np_(xg), tag + "_zback": np_(z_back), tag + "_delta_logp": np_(dl),
+                  tag + "_logp": np_(lp), tag + "_grad": np_(gl), tag + "_lap": np_(ll),
+                  tag + "_eloc": np_(kin + pot),
+                  tag + "_g_eta_w1": np_(eta.fc1.weight.grad)[:, 0], tag + "_g_eta_b1": np_(eta.fc1.bias.grad),
+                  tag + "_g_eta_w2": np_(eta.fc2.weight.grad)[0],
+                  tag + "_g_mu_w1": np_(mu.fc1.weight.grad)[:, 0], tag + "_g_mu_b1": np_(mu.fc1.bias.grad),
+                  tag + "_g_mu_w2": np_(mu.fc2.weight.grad)[0]})
+        print(tag, "done in %.0f s" % (time.time() - t0), flush=True)
+
+    set_solver(method="rk4", options=dict(step_size=1.0 / 16))
+    run("rk4s16")
+    set_solver(rtol=1e-9, atol=1e-11)
+    run("tight")
+    np.savez(os.path.join(OUT, "pipeline_n20.npz"), **d)
+    print("N = 20 golden fixture written")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "n20":
+        main_n20()
+    else:
+        main()

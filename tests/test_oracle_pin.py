@@ -144,3 +144,30 @@ def test_reference_port_matches_reference_default(golden):
     grads = torch.autograd.grad((lpf * T(g["weights"])).sum(), leaves)
     for a, k in zip(grads, ("eta_w1", "eta_b1", "eta_w2", "mu_w1", "mu_b1", "mu_w2")):
         close(a, g["default_g_" + k], 1e-9, 1e-13)
+
+
+def test_headline_config_n20_pinned(golden):
+    """The benchmark configuration (N = 20, 10 up / 10 down, Deta = Dmu = 50, 16 RK4 steps) on the real reference
+    (oracle/gen_golden.py n20): forward quantities of the same discrete flow to rounding; the reference's
+    adjoint-based gradient / Laplacian / E_loc on the same 16-step grid agree with the oracle's exact discrete
+    derivatives to 3e-12 / 9e-13 / 8e-14 (measured); the adaptive reference at rtol 1e-9 against the 64-step oracle
+    to ~1e-11."""
+    g = golden("pipeline_n20")
+    up, dn, eta, mu, ts = _model(g)
+    assert len(up) == 10 and len(dn) == 10 and len(eta[0]) == 50
+    x = O.cnf_generate(T(g["z0"]), eta, mu, ts, 16)
+    close(x, g["rk4s16_x"], 1e-13)
+    xr = T(g["rk4s16_x"])
+    z, dl = O.cnf_delta_logp(xr, eta, mu, ts, 16)
+    close(z, g["rk4s16_zback"], 1e-13)
+    close(dl, g["rk4s16_delta_logp"], 1e-12, 1e-15)
+    r = O.local_energy(xr, up, dn, eta, mu, ts, 16, float(g["Z"]))
+    close(r["logp"], g["rk4s16_logp"], 1e-13)
+    close(r["grad"], g["rk4s16_grad"], 1e-10)
+    close(r["lap"], g["rk4s16_lap"], 1e-10)
+    close(r["eloc"], g["rk4s16_eloc"], 1e-11)
+    r = O.local_energy(T(g["tight_x"]), up, dn, eta, mu, ts, 64, float(g["Z"]))
+    close(r["logp"], g["tight_logp"], 1e-10)
+    close(r["grad"], g["tight_grad"], 1e-9)
+    close(r["lap"], g["tight_lap"], 1e-9)
+    close(r["eloc"], g["tight_eloc"], 1e-10)
