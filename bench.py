@@ -34,13 +34,18 @@ def parse():
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--walkers", type=int, default=65536, help="walkers per GPU")
+    p.add_argument("--walkers", type=int, default=65536,
+                   help="walkers of the whole job (strong scaling: split over the GPUs) / per GPU (weak scaling)")
+    p.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                   help="strong (BASELINE configs[2]: 65536 walkers sharded over 1/2/4/8 GPUs) or weak (--walkers per GPU)")
     p.add_argument("--nup", type=int, default=10)
     p.add_argument("--ndown", type=int, default=10)
     p.add_argument("--hidden", type=int, default=50, help="Deta = Dmu (reference default 50)")
     p.add_argument("--Z", type=float, default=2.0)
     p.add_argument("--ode-steps", type=int, default=16, help="RK4 steps across t_span")
-    p.add_argument("--ref-walkers", type=int, default=4, help="walkers per step of the CPU reference arm")
+    p.add_argument("--ref-walkers", type=int, default=32,
+                   help="walkers per step of the CPU reference arm (a second, 4x smaller batch is timed beside it so "
+                        "that the saturation of the CPU throughput with the batch is visible)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
 
@@ -131,9 +136,9 @@ def run_ours(args):
     import ctypes as C
 
     model = build_model(args, dev)
-    model.basedist.manual_seed(1000 + rank)
+    model.basedist.manual_seed(1000)          # FreeFermion offsets the Philox walker index by rank * B
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    B = args.walkers
+    B = args.walkers // world if args.scaling == "strong" else args.walkers      # walkers of this rank
     params = list(model.parameters())
     nparam = sum(p.numel() for p in params)
 
@@ -171,6 +176,7 @@ def run_ours(args):
     peak = C.c_double()
     L.check(L.lib().ff_fp64_peak(20000, C.byref(peak), None))
     eloc_events.clear()
+    launches0 = L.lib().ff_launch_count()
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -181,6 +187,7 @@ def run_ours(args):
         E = step()
     t1.record()
     barrier()
+    launches = L.lib().ff_launch_count() - launches0
     ms = t0.elapsed_time(t1)
     eloc_ms = sum(a.elapsed_time(b) for a, b in eloc_events) / max(len(eloc_events), 1)
 
@@ -203,8 +210,7 @@ def run_ours(args):
         opt.zero_grad(set_to_none=True)
         gradE.backward()
         model.allreduce_gradients()
-        flat = torch.cat([p.grad.reshape(-1) for p in params] +
-                         [torch.tensor([model.E, model.E_std], device=dev)])
+        flat = torch.cat([p.grad.reshape(-1) for p in params] + [model.observables_device()])
         host_out.copy_(flat, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     e1.record()
@@ -236,9 +242,8 @@ def run_ours(args):
     total_walkers = B * world * args.steps
     value = total_walkers / (ms * 1e-3)
     n = args.nup + args.ndown
-    tables_on = os.environ.get("FF_NO_TABLE") is None
+    tables_on = L.get_option("no_table") == 0
     fl = flops_per_walker_eloc(n, args.hidden, args.hidden, args.ode_steps, tables=tables_on) * B
-    fl_ref = flops_per_walker_eloc(n, args.hidden, args.hidden, args.ode_steps, tables=False) * B
     by = hbm_bytes_per_walker_eloc(n, True, args.ode_steps) * B
     peaks = {}
     try:
@@ -249,15 +254,15 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "ground-state 2D quantum dot N=%d (%d up/%d down), %d walkers per GPU, Z=%.1f, "
-                               "Deta=Dmu=%d, %d RK4 steps" % (n, args.nup, args.ndown, B, args.Z, args.hidden, args.ode_steps),
-                   "walkers_per_gpu": B, "ode_steps": args.ode_steps,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "ground-state 2D quantum dot N=%d (%d up/%d down), %d walkers in total (%d per GPU), Z=%.1f, "
+                               "Deta=Dmu=%d, %d RK4 steps" % (n, args.nup, args.ndown, B * world, B, args.Z, args.hidden, args.ode_steps),
+                   "walkers_total": B * world, "walkers_per_gpu": B, "ode_steps": args.ode_steps,
                    "l2_policy": "inputs larger than L2 (per step: 21 MB coordinates, >20 GB stash streamed)",
                    "parallelism": "walkers sharded, dp%d" % world},
         "e2e": {"value": total_walkers / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": nparam * 8, "d2h_bytes_per_step": (nparam + 2) * 8},
-        "gpu_launches": 15 * args.steps,   # metropolis, generate + 2 table kernels, eloc + 2 table kernels, slater, adjoint, distance histogram + 3 binned-gradient kernels, direct pgrad + finish (device-side early exit)
+        "gpu_launches": int(launches),     # counted by the library (ff_launch_count) over the timed steps of this rank
         "clocks": sampler.summary(),
         "breakdown_ms": {k: round(v, 2) for k, v in bd.items()},
         "roofline": {"bound": "fp64", "kernel": "ff::eloc2_kernel<20,1> (E_loc sweep)", "achieved": fl / (eloc_ms * 1e-3) / 1e12,
@@ -265,8 +270,6 @@ def run_ours(args):
                      "peak_source": "ff_fp64_peak DFMA microbenchmark on this device (MEASURED_PEAKS.json has no fp64 entry)",
                      "flops_counted": "executed formulation (radial functions from certified Taylor tables)" if tables_on
                                       else "reference formulation (every hidden unit evaluated)",
-                     "reference_formulation": {"tflops_equivalent": fl_ref / (eloc_ms * 1e-3) / 1e12,
-                                               "frac_equivalent": fl_ref / (eloc_ms * 1e-3) / peak.value},
                      # ncu --set full (profiles/r01_eloc_ncu_full.md): 3.211 GB written + 0.021 GB read for 9472 walkers
                      "traffic": 3.2323e9 / 9472 * B if (n == 20 and args.hidden == 50 and args.ode_steps == 16) else None,
                      "traffic_source": "ncu dram__bytes_read+write, 9472-walker capture scaled per walker",
@@ -277,46 +280,73 @@ def run_ours(args):
     }
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args, budget_s=25.0)
+            line["cpu_baseline"] = cpu_baseline(args, budget_s=40.0)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def _ref_note(n):
+    return ("reference algorithm ported to torch-CPU (oracle/reference_port.py: dopri5 rtol 1e-6 + continuous adjoint + "
+            "2N nested autograd passes, N=%d); /root/reference is plain Python and needs the absent torchdiffeq" % n)
+
+
 def cpu_baseline(args, budget_s):
-    """The reference's own algorithm (adaptive dopri5, adjoint, nested-autograd Laplacian)
-    ported to torch-CPU (oracle/reference_port.py), one VMC iteration on a small batch."""
+    """The reference's own algorithm (adaptive dopri5, adjoint, nested-autograd Laplacian) ported to torch-CPU
+    (oracle/reference_port.py): one VMC iteration at two batch sizes, so that the saturation of the CPU throughput
+    with the batch is visible (the reference's default batch is 8000, FermionHO2D.py:30; its per-walker cost falls
+    with the batch until the BLAS / autograd overheads are amortised)."""
     from oracle import reference_port as R
     torch.set_num_threads(os.cpu_count() or 1)
-    walkers = args.ref_walkers
-    t = R.time_vmc_iteration(args.nup, args.ndown, args.hidden, args.Z, walkers, seed=7)
-    return {"value": walkers / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "1 VMC iteration of %d walkers, N=%d, reference algorithm (dopri5 rtol 1e-6 + adjoint + "
-                      "2N nested autograd passes), %.1f s" % (walkers, args.nup + args.ndown, t)}
+    n = args.nup + args.ndown
+    R.time_vmc_iteration(args.nup, args.ndown, args.hidden, args.Z, 1, seed=1, equil=2)       # warm-up (thread pools, allocator)
+    small = max(2, args.ref_walkers // 8)
+    t_small = R.time_vmc_iteration(args.nup, args.ndown, args.hidden, args.Z, small, seed=7)
+    # second point: as large as the budget allows (cost grows ~ batch^0.6 in this range), at most --ref-walkers / 2
+    big = small
+    while big * 2 <= max(args.ref_walkers // 2, small) and t_small * (big * 2 / small) ** 0.6 < budget_s:
+        big *= 2
+    pts = [{"walkers": small, "value": small / t_small, "seconds": round(t_small, 1)}]
+    if big > small:
+        t_big = R.time_vmc_iteration(args.nup, args.ndown, args.hidden, args.Z, big, seed=8)
+        pts.append({"walkers": big, "value": big / t_big, "seconds": round(t_big, 1)})
+    best = max(pts, key=lambda q: q["value"])
+    return {"value": best["value"], "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "ref_walkers": best["walkers"], "batch_points": pts,
+            "sample": "1 VMC iteration of %d walkers (and one of %d) of the %s" % (best["walkers"], pts[0]["walkers"], _ref_note(n))}
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU path on the host cores, K timed steps of `--ref-walkers` walkers (reduced
+    only if K steps would not fit ~4 minutes), plus one step at a quarter of that batch as a second data point."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     from oracle import reference_port as R
     torch.set_num_threads(os.cpu_count() or 1)
-    walkers = args.ref_walkers
     n = args.nup + args.ndown
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(max(1, min(args.warmup, 1))):
         R.time_vmc_iteration(args.nup, args.ndown, args.hidden, args.Z, 1, seed=1, equil=2)
+    small = max(2, args.ref_walkers // 4)
+    t_small = R.time_vmc_iteration(args.nup, args.ndown, args.hidden, args.Z, small, seed=5)
+    walkers = args.ref_walkers
+    while walkers > small and args.steps * t_small * (walkers / small) ** 0.6 > 240.0:
+        walkers //= 2
     ts = [R.time_vmc_iteration(args.nup, args.ndown, args.hidden, args.Z, walkers, seed=10 + i) for i in range(args.steps)]
     tot = sum(ts)
     value = walkers * args.steps / tot
+    pts = [{"walkers": small, "value": small / t_small, "seconds": round(t_small, 1)},
+           {"walkers": walkers, "value": value, "seconds": round(tot / args.steps, 1)}]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "ground-state 2D quantum dot N=%d (%d up/%d down), Z=%.1f, Deta=Dmu=%d; bounded sample of "
-                               "%d walkers per step on the host CPU" % (n, args.nup, args.ndown, args.Z, args.hidden, walkers)},
+                               "%d walkers per step on the host CPU" % (n, args.nup, args.ndown, args.Z, args.hidden, walkers),
+                   "ref_walkers": walkers, "cores": torch.get_num_threads()},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": "%d VMC iterations of %d walkers (reference algorithm ported to torch-CPU: "
-                                   "oracle/reference_port.py)" % (args.steps, walkers)},
+                         "ref_walkers": walkers, "batch_points": pts,
+                         "sample": "%d VMC iterations of %d walkers (and one of %d) of the %s" % (args.steps, walkers, small, _ref_note(n))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))

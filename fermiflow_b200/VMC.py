@@ -43,29 +43,73 @@ class _LogpFromSweep(torch.autograd.Function):
         return res.logp.clone()
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         res = ctx.res
+        if res.stash is None:
+            raise RuntimeError("the adjoint stash of this sweep was released by an earlier backward(): "
+                               "run the forward pass again (retain_graph is not supported on the fused path)")
         B = g.shape[0]
         z = res.z.detach().requires_grad_(True)
         with torch.enable_grad():
             lp0 = _FreeFermionLogp.apply(z, ctx.orb, ctx.ws, *ctx.nud)
         g0, = torch.autograd.grad(lp0, z, grad_outputs=g.contiguous())
         _, gparams = _backward_through_flow(ctx.owner.cnf, res.model, res.stash, B, g0, -g, False)
+        res.stash = None            # 22 GB at 65536 walkers, N = 20: free it now, not when the graph dies
         return (None, None, None, None, None, None, *gparams)
 
 
-def _global_mean_std(v):
-    """mean and unbiased std of v over all ranks (3-number all-reduce)."""
-    s = torch.stack([v.sum(), (v * v).sum(), torch.tensor(float(v.numel()), device=v.device, dtype=v.dtype)])
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(s)
-    tot, tot2, cnt = s.tolist()
+def _multi_rank():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def _moments(*vs):
+    """[sum v, sum v^2] of each vector plus the local count, as ONE device vector (no host synchronisation)."""
+    v0 = vs[0]
+    parts = []
+    for v in vs:
+        parts += [v.sum(), (v * v).sum()]
+    parts.append(torch.tensor(float(v0.numel()), device=v0.device, dtype=v0.dtype))
+    return torch.stack(parts)
+
+
+def _mean_std(tot, tot2, cnt):
+    """mean and unbiased standard deviation from the (all-reduced) sums -- device tensors."""
     mean = tot / cnt
-    var = max(tot2 - cnt * mean * mean, 0.0) / max(cnt - 1.0, 1.0)
-    return mean, var ** 0.5, cnt
+    var = (tot2 - cnt * mean * mean).clamp_min(0.0) / (cnt - 1.0).clamp_min(1.0)
+    return mean, var.sqrt()
+
+
+def _global_mean_std(v):
+    """mean and unbiased std of v over all ranks (3-number all-reduce) as Python floats, and the global count."""
+    s = _moments(v)
+    if _multi_rank():
+        dist.all_reduce(s)
+    mean, std = _mean_std(s[0], s[1], s[2])
+    return mean.item(), std.item(), s[2].item()
 
 
 class _VMCBase(torch.nn.Module):
+    """Observables (E, E_std, ...) are kept as device scalars and copied to the host, all in one transfer, the first
+    time one of them is read: forward() itself never waits for the GPU, so the backward pass and the optimiser step
+    are queued behind the sweep without a gap (the reference calls .item() inside forward, VMC.py:56)."""
+
+    _OBSERVABLES = ()
+
+    def _set_observables(self, **dev):
+        self._obs_dev, self._obs_host = dev, None
+
+    def observables_device(self):
+        """The observables of the last forward() as one device vector, in the order of their definition (no
+        host synchronisation)."""
+        return torch.stack([v.reshape(()) for v in self._obs_dev.values()])
+
+    def _observable(self, name):
+        if self._obs_host is None:
+            keys = list(self._obs_dev)
+            self._obs_host = dict(zip(keys, torch.stack([self._obs_dev[k].reshape(()) for k in keys]).tolist()))
+        return self._obs_host[name]
+
     def allreduce_gradients(self):
         """Sum the parameter gradients over ranks (call between backward() and step())."""
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
@@ -81,8 +125,14 @@ class _VMCBase(torch.nn.Module):
             o += g.numel()
 
 
+def _observable_property(name):
+    return property(lambda self: self._observable(name))
+
+
 class GSVMC(_VMCBase):
     """Ground-state VMC (VMC.py:4-61)."""
+
+    E, E_std = _observable_property("E"), _observable_property("E_std")
 
     def __init__(self, nup, ndown, orbitals, basedist, cnf, pair_potential, sp_potential=None):
         super().__init__()
@@ -114,17 +164,56 @@ class GSVMC(_VMCBase):
         _, x = self.sample((batch,))
         res = self.local_energy(x, stash=True)
         Eloc = res.eloc
-        self.E, self.E_std, nglobal = _global_mean_std(Eloc)
-        self.last = res
+        s = _moments(Eloc)
+        if _multi_rank():
+            dist.all_reduce(s)
+        nglobal = s[2]
+        E, E_std = _mean_std(s[0], s[1], nglobal)
+        self._set_observables(E=E, E_std=E_std)
+        self.last = res.without_stash()
         logp_full = _LogpFromSweep.apply(self, res, self._orb(x.device), None, self.nup, self.ndown,
                                          *_flat_params(self.cnf.v))
         # sum / global count == mean over all ranks once the gradients are all-reduced
-        gradE = (logp_full * (Eloc - self.E)).sum() / nglobal
+        gradE = (logp_full * (Eloc - E)).sum() / nglobal
         return gradE
+
+
+def _beta_estimators(Eloc, sl, log_state_weights, beta, local_cnt):
+    """VMC.py:139-171 on this rank's walkers (sl: sorted state index per walker, local_cnt: walkers per state).
+    Returns the observables (device scalars), the global walker count, gradF_phi (VMC.py:162, scalar with graph to
+    log_state_weights) and the per-walker mean of E_loc over all walkers of the same state (VMC.py:164-168)."""
+    NS = log_state_weights.shape[0]
+    logp_all = torch.log_softmax(log_state_weights, dim=0)
+    logp_states = logp_all.detach()[sl]
+    Floc = Eloc + logp_states / beta
+    # every cross-rank quantity of the iteration in ONE all-reduce: moments of E_loc, F_loc and log p(state),
+    # and per state the sum of E_loc and the number of walkers
+    zeros = torch.zeros(NS, dtype=Eloc.dtype, device=Eloc.device)
+    red = torch.cat([_moments(Eloc, Floc, logp_states), zeros.index_add(0, sl, Eloc), local_cnt])
+    if _multi_rank():
+        dist.all_reduce(red)
+    nglobal = red[6]
+    E, E_std = _mean_std(red[0], red[1], nglobal)
+    F, F_std = _mean_std(red[2], red[3], nglobal)
+    lpa = logp_all.detach()
+    obs = dict(E=E, E_std=E_std, F=F, F_std=F_std, S=-red[4] / nglobal, S_analytical=-(lpa * lpa.exp()).sum(),
+               logp_states_all=lpa)
+    ssum, cnt = red[7:7 + NS], red[7 + NS:7 + 2 * NS]
+    # sum_w logp_all[state_w] (Floc_w - F) = sum_s logp_all[s] (sum_{w in s} Floc_w - F count_s): autograd never
+    # sees a batch-fold duplicated gather; as everywhere, local sums / the global walker count become the global
+    # mean once the gradients are all-reduced
+    wstate = zeros.index_add(0, sl, Floc) - F * local_cnt
+    gradF_phi = (logp_all * wstate).sum() / nglobal
+    Eloc_x_mean = (ssum / cnt.clamp_min(1.0))[sl]
+    return obs, nglobal, gradF_phi, Eloc_x_mean
 
 
 class BetaVMC(_VMCBase):
     """Finite-temperature VMC (VMC.py:63-171)."""
+
+    E, E_std = _observable_property("E"), _observable_property("E_std")
+    F, F_std = _observable_property("F"), _observable_property("F_std")
+    S, S_analytical = _observable_property("S"), _observable_property("S_analytical")
 
     def __init__(self, beta, nup, ndown, deltaE, boltzmann, orbitals, basedist, cnf,
                  pair_potential, sp_potential=None):
@@ -183,32 +272,12 @@ class BetaVMC(_VMCBase):
         _, x = self.sample((batch,))
         table, state = self._state_table(x.device), self.state_indices
         res = eloc_sweep(self.cnf, x, table, state, self.nup, self._Z, self._harmonic, stash=True)
-        self.last = res
+        self.last = res.without_stash()
         Eloc = res.eloc
-        self.E, self.E_std, nglobal = _global_mean_std(Eloc)
-
-        logp_all = torch.log_softmax(self.log_state_weights, dim=0)
-        logp_states = logp_all[state.long()]
-        Floc = Eloc + logp_states.detach() / self.beta
-        self.F, self.F_std, _ = _global_mean_std(Floc)
-        self.S = -_global_mean_std(logp_states.detach())[0]
-        self.logp_states_all = logp_all.detach()
-        self.S_analytical = -(self.logp_states_all * self.logp_states_all.exp()).sum().item()
-
-        # sum_w logp_all[state_w] (Floc_w - F) = sum_s logp_all[s] * (sum of the weights of the walkers in s): the
-        # per-state sums are one index_add_, and autograd never sees an 8000-fold duplicated gather (VMC.py:159)
-        wstate = torch.zeros(self.Nstates, dtype=Eloc.dtype, device=Eloc.device).index_add_(0, state.long(), Floc - self.F)
-        gradF_phi = (logp_all * wstate).sum() / nglobal
-
-        # E_loc minus its mean over the walkers that share a state (VMC.py:163-168)
-        sl = state.long()
-        ssum = torch.zeros(self.Nstates, dtype=Eloc.dtype, device=Eloc.device).index_add_(0, sl, Eloc)
-        cnt = self.state_counts.to(Eloc.dtype)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            both = torch.stack([ssum, cnt])
-            dist.all_reduce(both)
-            ssum, cnt = both[0], both[1]
-        Eloc_x_mean = (ssum / cnt.clamp_min(1.0))[sl]
+        obs, nglobal, gradF_phi, Eloc_x_mean = _beta_estimators(Eloc, state.long(), self.log_state_weights, self.beta,
+                                                                self.state_counts.to(Eloc.dtype))
+        self.logp_states_all = obs.pop("logp_states_all")
+        self._set_observables(**obs)
         logp_full = _LogpFromSweep.apply(self, res, table, state, self.nup, self.ndown, *_flat_params(self.cnf.v))
         gradF_theta = (logp_full * (Eloc - Eloc_x_mean)).sum() / nglobal
         return gradF_phi, gradF_theta

@@ -27,6 +27,9 @@ _M = C.POINTER(FFModel)
 SIGNATURES = {
     "ff_version": ([], C.c_int),
     "ff_last_error": ([], C.c_char_p),
+    "ff_launch_count": ([], C.c_longlong),
+    "ff_set_option": ([C.c_char_p, _I], C.c_int),
+    "ff_get_option": ([C.c_char_p, C.POINTER(_I)], C.c_int),
     "ff_backflow": ([_M, _P, _LL, _P, _P, _P], C.c_int),
     "ff_cnf_generate": ([_M, _P, _LL, _I, _P, _P], C.c_int),
     "ff_cnf_delta_logp": ([_M, _P, _LL, _P, _P, _P, _P, _P], C.c_int),
@@ -34,6 +37,7 @@ SIGNATURES = {
     "ff_slater_logabsdet": ([_P, _LL, _I, _P, _P, _P, _P, _P, _P], C.c_int),
     "ff_free_fermion_logp": ([_P, _LL, _I, _I, _P, _P, _P, _P, _P], C.c_int),
     "ff_free_fermion_logp_lap": ([_P, _LL, _I, _I, _P, _P, _P, _P, _P, _P], C.c_int),
+    "ff_slater_hvp": ([_P, _LL, _I, _I, _P, _P, _D, _P, _P, _P], C.c_int),
     "ff_metropolis": ([_LL, _I, _I, _P, _P, _I, _D, C.c_ulonglong, _LL, _P, _P, _P, _P, _P, _P], C.c_int),
     "ff_eloc": ([_M, _P, _LL, _P, _P, _D, _I] + [_P] * 10 + [_P], C.c_int),
     "ff_logp_backward": ([_M, _LL] + [_P] * 12 + [_P], C.c_int),
@@ -62,6 +66,40 @@ def lib():
             fn.argtypes, fn.restype = args, res
         _lib = L
     return _lib
+
+
+def set_option(name, value):
+    """Kernel-variant switch of the library (include/fermiflow_b200.h ff_set_option); 0 = default."""
+    check(lib().ff_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    v = C.c_int()
+    check(lib().ff_get_option(name.encode(), C.byref(v)))
+    return v.value
+
+
+class options:
+    """with options(flow_cta=1, ...): ... -- sets the switches and restores the previous values."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        self.old = {k: get_option(k) for k in self.kw}
+        for k, v in self.kw.items():
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            set_option(k, v)
+        return False
+
+
+# Python-side switch: keep the per-item radial functions (f, f', f'') in the adjoint stash (16x the memory of the
+# stage inputs, 28 ms faster backward at 65536 walkers, N = 20).  Set to False to recompute them in the backward sweep.
+STASH_RADIAL = True
 
 
 def check(code):

@@ -5,7 +5,7 @@ import torch
 
 from . import _lib as L
 from .orbitals import orbital_indices
-from .slater import walker_states_from_collection
+from .slater import _SlaterGradient, walker_states_from_collection
 
 
 class BaseDist(object):
@@ -24,13 +24,17 @@ class _FreeFermionLogp(torch.autograd.Function):
                                              L.ptr(walker_state, torch.int32) if walker_state is not None else None,
                                              L.ptr(out), L.ptr(grad), L.stream()))
         if grad is not None:
-            ctx.save_for_backward(grad.reshape(shape))
+            ctx.save_for_backward(x, grad.reshape(shape))
+            ctx.meta = (orb, walker_state, n_up, n_dn)
         return out.reshape(shape[:-2])
 
     @staticmethod
     def backward(ctx, g):
-        dlog, = ctx.saved_tensors
-        return g[..., None, None] * dlog, None, None, None, None
+        # differentiable again (Hessian-vector product kernel), like the reference's log_prob (base_dist.py:48-56
+        # through slater.py:40-60)
+        x, dlog = ctx.saved_tensors
+        d = _SlaterGradient.apply(x, dlog, *ctx.meta, 2.0)
+        return g[..., None, None] * d, None, None, None, None
 
 
 def _state_table(states, device):
@@ -38,10 +42,24 @@ def _state_table(states, device):
     return torch.stack(rows).contiguous()
 
 
+def _rank_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 class FreeFermion(BaseDist):
+    """Random numbers: the Metropolis kernel draws from Philox4x32-10 with key = seed of the call and counter =
+    (GLOBAL walker index, step, particle).  The seed defaults to torch.initial_seed() at the first sample() (so
+    torch.manual_seed() controls the chains, as it does for the reference's torch.randn sampler) and advances
+    with every call; manual_seed(s) fixes it explicitly.  Under torch.distributed rank r samples the global walkers
+    [r B, (r + 1) B): ranks never share a stream, whatever the seed, and a W-rank run of B walkers each draws
+    the same chains as one rank with W B walkers."""
+
     def __init__(self, device=torch.device("cuda")):
         self.device = torch.device(device)
-        self.seed = 0x5EED
+        self.seed = None
         self._calls = 0
 
     def manual_seed(self, seed):
@@ -72,11 +90,14 @@ class FreeFermion(BaseDist):
         x0 = nrm = uni = None
         if noise is not None:
             x0, nrm, uni = (t.contiguous() for t in noise)
+        if self.seed is None:
+            self.seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
         seed = (self.seed + 0x9E3779B97F4A7C15 * self._calls) & 0xFFFFFFFFFFFFFFFF
         self._calls += 1
+        rank, _ = _rank_world()
         L.check(L.lib().ff_metropolis(B, n_up, n_dn, L.ptr(orb, torch.int32),
                                       L.ptr(walker_state, torch.int32) if walker_state is not None else None,
-                                      int(steps), float(tau), seed, 0, L.ptr(x0), L.ptr(nrm), L.ptr(uni),
+                                      int(steps), float(tau), seed, rank * B, L.ptr(x0), L.ptr(nrm), L.ptr(uni),
                                       L.ptr(x), None, L.stream()))
         return x
 

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
 
 #include "../../include/fermiflow_b200.h"
 #include "ff_adjoint.cuh"
@@ -12,7 +13,6 @@
 #include "ff_flow.cuh"
 #include "ff_flow_warp.cuh"
 #include "ff_eloc2.cuh"
-#include "ff_eloc3.cuh"
 #include "ff_misc.cuh"
 #include "ff_metro_reg.cuh"
 
@@ -32,10 +32,46 @@ int cuda_fail(cudaError_t e, const char* what) {
     return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
 }
 
+// "this launcher does not apply, try the next one" -- outside the range of cudaError_t (>= 0) and of the argument /
+// capacity errors reported to the caller (-1, -2)
+constexpr int FF_FALLBACK = -1000;
+
+// Kernel-variant switches (tests, A/B timing): set explicitly through ff_set_option, process-wide atomics.  The
+// library never reads the environment.  0 = default behaviour for every option.
+enum Opt {
+    OPT_NO_TABLE,            // evaluate every hidden unit instead of the certified Taylor tables
+    OPT_NO_W_BALANCE,        // several walkers per CTA: do not rebalance the walkers over the rounds
+    OPT_NO_RT_CACHE,         // no shared-memory mirror of the head of the eta table
+    OPT_FLOW_WARP_FILL,      // per cent of lanes the pair items must fill for the warp-per-walker sweeps (0 -> 60)
+    OPT_FLOW_CTA,            // CTA-synchronous flow sweeps instead of warp-per-walker
+    OPT_FLOW_BIG,            // 128-register build of the CTA-synchronous sweeps
+    OPT_ELOC_GENERIC,        // generic flow_kernel<MODE_ELOC> instead of the statically specialised eloc kernels
+    OPT_SLATER_CTA,          // CTA-cooperative Slater kernel instead of warp-per-walker
+    OPT_METROPOLIS_KERNEL,   // 0 auto, 1 registers (thread per walker), 2 warp per walker, 3 thread per walker (shared memory)
+    OPT_ADJOINT_CTA,         // CTA-synchronous adjoint sweep
+    OPT_PGRAD_DIRECT,        // direct parameter-gradient kernel (every hidden unit) instead of binned Taylor moments
+    OPT_PGRAD_TILE,          // walker-stages per tile of the binned kernel (0 -> 32)
+    OPT_PGRAD_FIXED_RANGE,   // eta nodes over the fixed range instead of the sampled 99.9 % quantile
+    OPT_COUNT
+};
+const char* const kOptNames[OPT_COUNT] = {
+    "no_table", "no_w_balance", "no_rt_cache", "flow_warp_fill", "flow_cta", "flow_big", "eloc_generic", "slater_cta",
+    "metropolis_kernel", "adjoint_cta", "pgrad_direct", "pgrad_tile", "pgrad_fixed_range"};
+std::atomic<int> g_opt[OPT_COUNT];
+inline int opt(Opt o) { return g_opt[o].load(std::memory_order_relaxed); }
+
 #define FF_CUDA(call)                                         \
     do {                                                      \
         cudaError_t e__ = (call);                             \
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+// every kernel launch of the library is counted (ff_launch_count: the "gpu_launches" figure of bench.py)
+std::atomic<long long> g_launches{0};
+#define FF_LAUNCHED()                                  \
+    do {                                               \
+        g_launches.fetch_add(1, std::memory_order_relaxed); \
+        FF_CUDA(cudaGetLastError());                   \
     } while (0)
 
 struct DevInfo { int sms = 0; int smem_optin = 0; int smem_sm = 0; int smem_reserved = 1024; bool ok = false; };
@@ -70,13 +106,13 @@ inline int even(int x) { return (x + 1) & ~1; }
 
 // Certified Taylor tables of the radial functions for one sweep launch (ff_radial_table.cuh): built from
 // the current parameters on the launch stream, released stream-ordered after the sweep.
-// FF_NO_TABLE=1 keeps the direct evaluation of every hidden unit.
+// Option "no_table" keeps the direct evaluation of every hidden unit.
 struct RadialTables {
     double* buf = nullptr;
     cudaStream_t st = nullptr;
     int build(const ff_model* m, cudaStream_t stream, ff::FlowArgs& a) {
         a.rt_eta = nullptr; a.rt_mu = nullptr;
-        if (getenv("FF_NO_TABLE") != nullptr) return 0;
+        if (opt(OPT_NO_TABLE)) return 0;
         st = stream;
         {   // keep the stream-ordered pool's memory across synchronisation points (default: trimmed at every sync)
             static thread_local bool pool_ready[16] = {};
@@ -97,9 +133,9 @@ struct RadialTables {
         b.w1[0] = m->eta_w1; b.b1[0] = m->eta_b1; b.w2[0] = m->eta_w2; b.H[0] = m->H_eta; b.table[0] = buf;
         b.w1[1] = m->mu_w1; b.b1[1] = m->mu_b1; b.w2[1] = m->mu_w2; b.H[1] = m->H_mu; b.table[1] = m->H_mu > 0 ? buf + per : nullptr;
         ff::radial_table_build_kernel<<<dim3(ff::kRtMaxNodes / 128, 2), 128, 0, st>>>(b);
-        FF_CUDA(cudaGetLastError());
+        FF_LAUNCHED();
         ff::radial_table_check_kernel<<<dim3(1, 2), 128, 0, st>>>(b.table[0], b.table[1]);
-        FF_CUDA(cudaGetLastError());
+        FF_LAUNCHED();
         a.rt_eta = b.table[0]; a.rt_mu = b.table[1];
         return 0;
     }
@@ -148,7 +184,7 @@ int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t
     if (threads < 64) threads = 64;
     // helper warp: its Gram matrix overlaps the MLP loop of the item warps (direct evaluation only; with the
     // Taylor tables the item phase is short and every warp shares the Gram matrix)
-    if (eloc && threads + 32 <= 256 && getenv("FF_NO_TABLE") != nullptr) threads += 32;
+    if (eloc && threads + 32 <= 256 && opt(OPT_NO_TABLE)) threads += 32;
     smem = (size_t)(common + (long long)W * a.wstride) * 8;
     return 0;
 }
@@ -163,7 +199,7 @@ int launch_flow_kernel(K kernel, ff::FlowArgs& a, int threads, size_t smem, cuda
     if (occ < 1) return fail(-2, "flow kernel does not fit on an SM (threads %d, smem %zu)", threads, smem);
     long long nb = (a.B + a.W - 1) / a.W;
     long long grid = (long long)di.sms * occ;
-    if (a.W > 1 && a.B > 0 && getenv("FF_NO_W_BALANCE") == nullptr) {
+    if (a.W > 1 && a.B > 0 && !opt(OPT_NO_W_BALANCE)) {
         // several walkers per CTA (small n): spread them evenly over the rounds the resident CTAs need anyway --
         // 8000 walkers at W = 26 are 308 tasks for 296 CTAs (two rounds, the second almost empty); W = 14 gives 572
         // tasks, two full rounds of half the length.  threads / smem were sized for the larger W and stay valid.
@@ -174,7 +210,7 @@ int launch_flow_kernel(K kernel, ff::FlowArgs& a, int threads, size_t smem, cuda
     if (grid > nb) grid = nb;
     if (grid < 1) return 0;
     kernel<<<(unsigned)grid, threads, smem, st>>>(a);
-    FF_CUDA(cudaGetLastError());
+    FF_LAUNCHED();
     return 0;
 }
 
@@ -187,10 +223,10 @@ int launch_flow_warp(ff::FlowArgs& a, cudaStream_t st) {
     int common = ff::kTabDoubles + 6 * (((a.H_eta + 3) & ~3) + ((a.H_mu + 3) & ~3));
     common = even(common) + 2 * ((a.NP + 7) / 8) + 2;
     size_t smem = (size_t)(common + (long long)warps * wg.slice) * 8;
-    if (smem > (size_t)di.smem_optin) return 1;
+    if (smem > (size_t)di.smem_optin) return FF_FALLBACK;
     {   // spare shared memory at FF_WARP_MINB CTAs per SM mirrors the head of the eta Taylor table
         const long long room = (long long)di.smem_sm / FF_WARP_MINB - di.smem_reserved - (long long)smem - 64;
-        a.rt_cache_nodes = (a.rt_eta != nullptr && room > 0 && getenv("FF_NO_RT_CACHE") == nullptr)
+        a.rt_cache_nodes = (a.rt_eta != nullptr && room > 0 && !opt(OPT_NO_RT_CACHE))
                                ? (int)std::min<long long>(room / (8 * ff::kRtCoef), 2048) : 0;
         smem += (size_t)a.rt_cache_nodes * 8 * ff::kRtCoef;
     }
@@ -199,11 +235,11 @@ int launch_flow_warp(ff::FlowArgs& a, cudaStream_t st) {
     FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     int occ = 0;
     FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * warps, smem));
-    if (occ < 1) return 1;
+    if (occ < 1) return FF_FALLBACK;
     long long grid = std::min<long long>((a.B + warps - 1) / warps, (long long)di.sms * occ);
     if (grid < 1) return 0;
     kernel<<<(unsigned)grid, 32 * warps, smem, st>>>(a);
-    FF_CUDA(cudaGetLastError());
+    FF_LAUNCHED();
     return 0;
 }
 
@@ -214,50 +250,17 @@ int launch_flow(ff::FlowArgs& a, int threads, size_t smem, cudaStream_t st) {
         const int rounds = (a.NP + 31) / 32;
         // measured (scripts/dev_gen_time_n.py, 65536 walkers): N = 12 (66 pairs, 69 % of three rounds) 7.0 ms CTA-synchronous
         // against 5.7 ms warp-per-walker; N = 9 (36 pairs, 56 %) 4.3 against 4.9 ms; N = 6 (15 pairs, 47 %) 2.0 against 3.8 ms
-        const int min_fill = getenv("FF_FLOW_WARP_FILL") ? atoi(getenv("FF_FLOW_WARP_FILL")) : 60;      // per cent of the lanes
-        if (a.NP > 0 && a.n <= 255 && 100 * a.NP >= min_fill * 32 * rounds && getenv("FF_FLOW_CTA") == nullptr) {
+        const int min_fill = opt(OPT_FLOW_WARP_FILL) ? opt(OPT_FLOW_WARP_FILL) : 60;      // per cent of the lanes
+        if (a.NP > 0 && a.n <= 255 && 100 * a.NP >= min_fill * 32 * rounds && !opt(OPT_FLOW_CTA)) {
             const int r = launch_flow_warp<MODE>(a, st);
-            if (r != 1) return r;
-        }
-    }
-    if (MODE == ff::MODE_ELOC && a.W == 1 && a.H_mu > 0 && getenv("FF_NO_STATIC") == nullptr) {
-        // statically specialised sweeps for the benchmark sizes (BASELINE.json configs)
-        if (a.n == 20) {
-            constexpr int t1 = ff::flow_geom(ff::MODE_ELOC, 20, true).threads1;
-            if (threads == t1 + 32) return launch_flow_kernel(ff::flow_kernel_eloc_static<20, 1, 1>, a, threads, smem, st);
-            if (threads == t1) return launch_flow_kernel(ff::flow_kernel_eloc_static<20, 1, 0>, a, threads, smem, st);
+            if (r != FF_FALLBACK) return r;
         }
     }
     if constexpr (MODE != ff::MODE_ELOC) {
-        if (threads <= 256 && getenv("FF_FLOW_BIG") == nullptr)
+        if (threads <= 256 && !opt(OPT_FLOW_BIG))
             return launch_flow_kernel(ff::flow_kernel_small<MODE>, a, threads, smem, st);
     }
     return launch_flow_kernel(ff::flow_kernel<MODE>, a, threads, smem, st);
-}
-
-// Warp-specialised two-walker pipeline (ff_eloc3.cuh): one CTA per SM.
-template <int SN, int SMU>
-int launch_eloc3(ff::FlowArgs& a, cudaStream_t st) {
-    constexpr ff::Eloc3Geom q = ff::eloc3_geom(SN, SMU != 0);
-    constexpr ff::Eloc2Geom g = q.g;
-    a.D = g.D; a.NP = g.NP; a.P = g.P; a.DP = g.DP; a.NV = g.NV; a.NSV = g.NSV; a.grec = ff::kGRec;
-    a.off_G = g.off_G; a.off_AM = g.off_AM; a.off_u = g.off_u; a.off_kLx = g.off_kLx; a.off_part = g.off_part;
-    a.off_x0 = g.off_x0; a.off_sl = g.off_sl; a.wstride = g.wstride; a.W = 1;
-    const int need = ff::slater_scratch_size(a.n_up, a.n - a.n_up) + 2 * g.D + g.n * g.n + g.NP + 8;
-    if (need > 2 * g.MAT) return fail(-2, "internal: finale scratch does not fit");
-    constexpr int NI = FF_ELOC3_ILP;
-    const int common = ff::kTabDoubles + 12 * (ff::half_rows<NI>(a.H_eta) + ff::half_rows<NI>(a.H_mu)) + 2 * ((g.NP + 7) / 8) + 4;
-    const size_t smem = (size_t)(common + 2 * g.wstride) * 8;
-    const DevInfo di = dev_info();
-    if ((long long)smem > di.smem_optin || q.threads > 1024) return 1;
-    auto kernel = ff::eloc3_kernel<SN, SMU>;
-    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long grid = (a.B + 1) / 2;
-    if (grid > di.sms) grid = di.sms;
-    if (grid < 1) return 0;
-    kernel<<<(unsigned)grid, q.threads, smem, st>>>(a);
-    FF_CUDA(cudaGetLastError());
-    return 0;
 }
 
 // Barrier-synchronous sweep with fused phases (ff_eloc2.cuh eloc2_kernel).
@@ -270,11 +273,11 @@ int launch_eloc2(ff::FlowArgs& a, cudaStream_t st) {
     a.off_x0 = g.off_x0; a.off_sl = g.off_sl; a.wstride = g.wstride; a.W = 1;
     const int need = ff::slater_scratch_size(a.n_up, a.n - a.n_up) + 2 * g.D + g.n * g.n + g.NP + 8;
     // finale scratch: the two RK partial buffers plus J1 (dead after the last stage; eloc2_kernel re-zeroes it)
-    if (need > 3 * g.MAT) return 1;            // the generic kernel takes over
+    if (need > 3 * g.MAT) return FF_FALLBACK;  // the generic kernel takes over
     constexpr int NI = FF_ELOC2_ILP;
     const int common = ff::kTabDoubles + 6 * (ff::coef_rows2<NI>(a.H_eta) + ff::coef_rows2<NI>(a.H_mu)) + 2 * ((g.NP + 7) / 8) + 2;
     size_t smem = (size_t)(common + g.wstride) * 8;
-    if ((long long)smem > dev_info().smem_optin) return 1;
+    if ((long long)smem > dev_info().smem_optin) return FF_FALLBACK;
     {   // what is left of this CTA's share of the SM mirrors the head of the eta table (96 bytes per node)
         const DevInfo di = dev_info();
         // ... without lowering the number of resident CTAs the register allocation aims at
@@ -287,32 +290,38 @@ int launch_eloc2(ff::FlowArgs& a, cudaStream_t st) {
     return launch_flow_kernel(ff::eloc2_kernel<SN, SMU>, a, q.threads, smem, st);
 }
 
-// Opt-in variants, N = 20, 65536 walkers: FF_ELOC_V3=1 (two-walker pipeline) 183 ms, FF_ELOC_V2=1 (fused phases,
-// barrier-synchronous) 185 ms, against 177 ms of the default flow_kernel_eloc_static.
-int try_eloc_pipeline(ff::FlowArgs& a, cudaStream_t st) {
-    if (getenv("FF_ELOC_V3") != nullptr && a.H_mu > 0 && a.n == 20) return launch_eloc3<20, 1>(a, st);
-    // With the Taylor tables the sweep is bound by the latency of the matrix phases and the fused-phase kernel
-    // with three helper warps wins (105 ms against 113 ms of flow_kernel_eloc_static at N = 20, 65536 walkers);
-    // with direct evaluation (FF_NO_TABLE=1) the 128-register static kernel does (177 ms against 185 ms).
-    // FF_ELOC_V1=1 / FF_ELOC_V2=1 force one or the other.
-    const bool v2 = getenv("FF_ELOC_V2") != nullptr || (a.rt_eta != nullptr && getenv("FF_ELOC_V1") == nullptr);
-    if (v2 && a.H_mu > 0) {
-        // statically specialised particle numbers (BASELINE.json configs: N = 6, 12, 20)
-        switch (a.n) {
-            case 20: return launch_eloc2<20, 1>(a, st);
-            case 12: return launch_eloc2<12, 1>(a, st);
-            case 6: return launch_eloc2<6, 1>(a, st);
-            default: break;
-        }
+// Statically specialised E_loc sweeps (ff_eloc2.cuh) for the particle numbers of the BASELINE.json configs; anything
+// else, or "eloc_generic", runs the generic flow_kernel<MODE_ELOC>.
+int try_eloc_static(ff::FlowArgs& a, cudaStream_t st) {
+    if (opt(OPT_ELOC_GENERIC) || a.H_mu <= 0) return FF_FALLBACK;
+    switch (a.n) {
+        case 20: return launch_eloc2<20, 1>(a, st);
+        case 12: return launch_eloc2<12, 1>(a, st);
+        case 6: return launch_eloc2<6, 1>(a, st);
+        default: return FF_FALLBACK;
     }
-    return 1;
 }
 
 }  // namespace
 
 extern "C" {
 
-int ff_version(void) { return 100; }
+int ff_version(void) { return 200; }
+
+long long ff_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int ff_set_option(const char* name, int value) {
+    if (!name) return fail(-1, "ff_set_option: null name");
+    for (int k = 0; k < OPT_COUNT; ++k)
+        if (strcmp(name, kOptNames[k]) == 0) { g_opt[k].store(value, std::memory_order_relaxed); return 0; }
+    return fail(-1, "ff_set_option: unknown option '%s'", name);
+}
+int ff_get_option(const char* name, int* value) {
+    if (!name || !value) return fail(-1, "ff_get_option: null argument");
+    for (int k = 0; k < OPT_COUNT; ++k)
+        if (strcmp(name, kOptNames[k]) == 0) { *value = opt((Opt)k); return 0; }
+    return fail(-1, "ff_get_option: unknown option '%s'", name);
+}
 const char* ff_last_error(void) { return g_err; }
 
 int ff_stash_sizes(const ff_model* m, long long B, long long* ny, long long* nc) {
@@ -375,8 +384,8 @@ int ff_eloc(const ff_model* m, const double* x, long long B, const int* orb, con
     if (int e = rt.build(m, (cudaStream_t)stream, a)) return e;
     {
         ff::FlowArgs a2 = a;
-        const int r = try_eloc_pipeline(a2, (cudaStream_t)stream);
-        if (r != 1) return r;
+        const int r = try_eloc_static(a2, (cudaStream_t)stream);
+        if (r != FF_FALLBACK) return r;
     }
     return launch_flow<ff::MODE_ELOC>(a, threads, smem, (cudaStream_t)stream);
 }

@@ -1,6 +1,5 @@
-// Building blocks of the second-generation E_loc sweep (used by the warp-specialised pipeline
-// in ff_eloc3.cuh): walker-block geometry with ping-pong J buffers, radial MLP with NI hidden
-// units in lock-step, two-partial 3/8-rule update.
+// Statically specialised E_loc sweep (eloc2_kernel) and its building blocks: walker-block geometry with
+// ping-pong J buffers, radial MLP with NI hidden units in lock-step, two-partial 3/8-rule update.
 //
 // Same mathematics as flow_body<MODE_ELOC> (ff_flow.cuh; replaces utils.py:44-65
 // y_grad_laplacian + VMC.py:41-55 on top of flow.py:42-56 / equivariant_funs.py:17-102).

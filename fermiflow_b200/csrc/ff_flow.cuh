@@ -779,10 +779,5 @@ __global__ void __launch_bounds__(512, 1) flow_kernel(const FlowArgs a) { flow_b
 template <int MODE>
 __global__ void __launch_bounds__(256, 4) flow_kernel_small(const FlowArgs a) { flow_body<MODE, 0, 0>(a); }
 
-// Statically specialised E_loc sweep (one walker per CTA, two CTAs per SM).
-// HELP = 1: one extra helper warp computes the Gram matrix while the item warps run the MLP loop (direct
-// evaluation); HELP = 0: every warp shares the Gram matrix (Taylor tables: the item phase is short).
-template <int SN, int SMU, int HELP = 1>
-__global__ void __launch_bounds__(256, 2) flow_kernel_eloc_static(const FlowArgs a) { flow_body<MODE_ELOC, SN, SMU, HELP>(a); }
 
 }  // namespace ff

@@ -293,6 +293,147 @@ __global__ void __launch_bounds__(256) slater_warp_kernel(const SlaterArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Hessian-vector product of scale * (log|det Phi_up| + log|det Phi_dn|): the double backward of
+// LogAbsSlaterDet / LogAbsSlaterDetMultStates (slater.py:40-60, 120-156 build their backward with
+// differentiable torch ops so that utils.py:44-65 can differentiate it again).  One warp per walker, any spin
+// block up to kMaxOrb particles (lane-strided loops):
+//   H_{ia,jb} = delta_ij C^{ab}_i - B^a_ij B^b_ji,   B^a = (d_a Phi) Phi^-1,   C^{ab}_i = sum_k d_a d_b phi_k(r_i) Phi^-1_ki
+//   (H v)_{ia} = sum_b C^{ab}_i v_ib - sum_j B^a_ij U_ji,      U_ji = sum_b B^b_ji v_jb.
+// ---------------------------------------------------------------------------------------
+struct SlaterHvpArgs {
+    int n, n_up;
+    long long B;
+    const double* x;
+    const int* orb;
+    const int* walker_state;
+    double scale;
+    const double* v;      // [B][n][2]
+    double* hv;           // [B][n][2]
+};
+__host__ __device__ inline int slater_hvp_slice(int nmax) {      // doubles of shared memory per warp
+    return ff_even(nmax * (2 * nmax + 1) + nmax * kHermStride + 3 * nmax * (nmax + 1) + 2);
+}
+
+__global__ void __launch_bounds__(128) slater_hvp_warp_kernel(const SlaterHvpArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int n = a.n, D = 2 * n;
+    const int nmax = max(a.n_up, n - a.n_up);
+    double* A = smem + (size_t)warp * slater_hvp_slice(nmax);          // [ns][2 ns + 1]
+    double* Ht = A + nmax * (2 * nmax + 1);                             // [ns][kHermStride]
+    double* Bx = Ht + nmax * kHermStride;                               // [ns][ns + 1]
+    double* By = Bx + nmax * (nmax + 1);
+    double* U = By + nmax * (nmax + 1);
+    const double inv_sqrt_pi = 0.56418958354775628695;
+    const long long wstride = (long long)gridDim.x * nwarp;
+    for (long long b = (long long)blockIdx.x * nwarp + warp; b < a.B; b += wstride) {
+        const int* orb = a.orb + (size_t)(a.walker_state ? a.walker_state[b] : 0) * n;
+        for (int s = 0; s < 2; ++s) {
+            const int ns = s ? n - a.n_up : a.n_up, i0 = s ? a.n_up : 0;
+            if (ns == 0) continue;
+            const int LD = 2 * ns + 1, LB = ns + 1;
+            for (int e = lane; e < 2 * ns; e += 32) {                   // 1D oscillator functions (orbitals.py:66-90)
+                const int i = e >> 1, c = e & 1;
+                const double x = a.x[b * D + 2 * (i0 + i) + c];
+                const double g = exp(-0.5 * x * x);
+                double* t = Ht + i * kHermStride + c * 24;
+                double hm = 0.0, hh = 1.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    t[3 * k] = hh * g;
+                    t[3 * k + 1] = (c_herm_d1[k] * hm - x * hh) * g;
+                    t[3 * k + 2] = (x * x - (2.0 * k + 1.0)) * hh * g;
+                    const double hn = c_herm_up[k] * x * hh - c_herm_dn[k] * hm;
+                    hm = hh; hh = hn;
+                }
+            }
+            __syncwarp();
+            for (int e = lane; e < ns * ns; e += 32) {                  // [Phi | I]
+                const int i = e / ns, k = e - i * ns;
+                const int id = orb[i0 + k];
+                const double* t = Ht + i * kHermStride;
+                A[i * LD + k] = inv_sqrt_pi * t[3 * c_orb_nx[id]] * t[24 + 3 * c_orb_ny[id]];
+                A[i * LD + ns + k] = (i == k) ? 1.0 : 0.0;
+            }
+            __syncwarp();
+            for (int k = 0; k < ns; ++k) {                              // Gauss-Jordan, partial pivoting
+                double best = -1.0;
+                int p = k;
+                for (int r = k + lane; r < ns; r += 32) {
+                    const double v = fabs(A[r * LD + k]);
+                    if (v > best) { best = v; p = r; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int op = __shfl_xor_sync(0xffffffffu, p, o);
+                    if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+                }
+                const double ipv = 1.0 / A[p * LD + k];
+                __syncwarp();
+                for (int c = lane; c < 2 * ns; c += 32) {               // swap rows k <-> p, scale row k
+                    const double vk = A[k * LD + c], vp = A[p * LD + c];
+                    A[p * LD + c] = vk;
+                    A[k * LD + c] = vp * ipv;
+                }
+                __syncwarp();
+                for (int c = lane; c < 2 * ns; c += 32) {               // eliminate column k from every other row
+                    if (c == k) continue;
+                    const double akc = A[k * LD + c];
+                    for (int r = 0; r < ns; ++r)
+                        if (r != k) A[r * LD + c] = fma(-A[r * LD + k], akc, A[r * LD + c]);
+                }
+                __syncwarp();
+            }
+            for (int e = lane; e < ns * ns; e += 32) {                  // B^x, B^y
+                const int i = e / ns, j = e - i * ns;
+                const double* t = Ht + i * kHermStride;
+                double bx = 0.0, by = 0.0;
+                for (int k = 0; k < ns; ++k) {
+                    const int id = orb[i0 + k];
+                    const double* tx = t + 3 * c_orb_nx[id];
+                    const double* ty = t + 24 + 3 * c_orb_ny[id];
+                    const double iv = inv_sqrt_pi * A[k * LD + ns + j];
+                    bx = fma(tx[1] * ty[0], iv, bx);
+                    by = fma(tx[0] * ty[1], iv, by);
+                }
+                Bx[i * LB + j] = bx;
+                By[i * LB + j] = by;
+            }
+            __syncwarp();
+            const double* vv = a.v + b * D + 2 * i0;
+            for (int e = lane; e < ns * ns; e += 32) {                  // U_ji = v_jx B^x_ji + v_jy B^y_ji
+                const int j = e / ns, i = e - j * ns;
+                U[j * LB + i] = fma(vv[2 * j], Bx[j * LB + i], vv[2 * j + 1] * By[j * LB + i]);
+            }
+            __syncwarp();
+            for (int i = lane; i < ns; i += 32) {
+                const double* t = Ht + i * kHermStride;
+                double cxx = 0.0, cxy = 0.0, cyy = 0.0;
+                for (int k = 0; k < ns; ++k) {
+                    const int id = orb[i0 + k];
+                    const double* tx = t + 3 * c_orb_nx[id];
+                    const double* ty = t + 24 + 3 * c_orb_ny[id];
+                    const double iv = inv_sqrt_pi * A[k * LD + ns + i];
+                    cxx = fma(tx[2] * ty[0], iv, cxx);
+                    cxy = fma(tx[1] * ty[1], iv, cxy);
+                    cyy = fma(tx[0] * ty[2], iv, cyy);
+                }
+                double hx = fma(cxx, vv[2 * i], cxy * vv[2 * i + 1]);
+                double hy = fma(cxy, vv[2 * i], cyy * vv[2 * i + 1]);
+                for (int j = 0; j < ns; ++j) {
+                    const double u = U[j * LB + i];
+                    hx = fma(-Bx[i * LB + j], u, hx);
+                    hy = fma(-By[i * LB + j], u, hy);
+                }
+                *reinterpret_cast<double2*>(a.hv + b * D + 2 * (i0 + i)) = make_double2(a.scale * hx, a.scale * hy);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Metropolis sampling of |Psi_0|^2 (base_dist.py:58-70, 103-134), one thread per walker.
 // Per-thread matrices live in shared memory, element e of thread t at sm[e * T + t].
 // ---------------------------------------------------------------------------------------

@@ -3,7 +3,6 @@
 RK4 CUDA kernels (C ABI ff_cnf_generate / ff_cnf_delta_logp / ff_eloc / ff_logp_backward).
 """
 import ctypes as C
-import os
 
 import torch
 
@@ -27,9 +26,9 @@ class _Stash:
         L.check(L.lib().ff_backward_work_size(C.byref(model), B, C.byref(nw)))
         self.y = torch.empty(ny.value, dtype=torch.float64, device=device)
         # the per-item radial functions (f, f', f''): 16x the size of the stage inputs (22 GB for 65536 walkers at
-        # n = 20).  FF_NO_STASH_C=1 drops them: the backward sweep then recomputes them from the stage inputs
-        # (Taylor tables), which costs 28 ms more per iteration at that size but 16x less memory.
-        self.c = None if os.environ.get("FF_NO_STASH_C") else torch.empty(nc.value, dtype=torch.float64, device=device)
+        # n = 20).  _lib.STASH_RADIAL = False drops them: the backward sweep then recomputes them from the stage
+        # inputs (Taylor tables), which costs 28 ms more per iteration at that size but 16x less memory.
+        self.c = torch.empty(nc.value, dtype=torch.float64, device=device) if L.STASH_RADIAL else None
         self.n_work = nw.value
 
 
@@ -68,7 +67,10 @@ class _DeltaLogp(torch.autograd.Function):
         return z, dl
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gz, gdl):
+        # first order only: the second derivatives of log p w.r.t. x come from the forward-mode sweep
+        # (utils.y_grad_laplacian / eloc_sweep, C ABI ff_eloc), not from differentiating this adjoint again
         B = ctx.B
         dev = ctx.stash.y.device
         gz = torch.zeros(B, ctx.model.n_up + ctx.model.n_dn, 2, dtype=torch.float64, device=dev) if gz is None else gz

@@ -25,20 +25,50 @@ def _run(x, orb, walker_state, want_grad, want_lap=False):
             lap.reshape(shape[:-2]) if want_lap else None)
 
 
+class _SlaterGradient(torch.autograd.Function):
+    """d(scale * (log|det_up| + log|det_dn|))/dx as a differentiable function of x: the forward hands out the
+    gradient the forward kernel already produced, the backward is the Hessian-vector product kernel
+    (C ABI ff_slater_hvp).  This is what makes the backward of the Slater primitives differentiable again, like the
+    reference's (slater.py:40-60 builds it from torch ops for utils.py:44-65)."""
+
+    @staticmethod
+    def forward(ctx, x, dlog, orb, walker_state, n_up, n_dn, scale):
+        ctx.save_for_backward(x)
+        ctx.meta = (orb, walker_state, n_up, n_dn, scale)
+        return dlog.clone()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, v):
+        x, = ctx.saved_tensors
+        orb, ws, n_up, n_dn, scale = ctx.meta
+        n = n_up + n_dn
+        xf = x.detach().reshape(-1, n, 2).contiguous()
+        vf = v.reshape(-1, n, 2).contiguous()
+        hv = torch.empty_like(xf)
+        L.check(L.lib().ff_slater_hvp(L.ptr(xf), xf.shape[0], n_up, n_dn, L.ptr(orb, torch.int32),
+                                      L.ptr(ws, torch.int32) if ws is not None else None, float(scale),
+                                      L.ptr(vf), L.ptr(hv), L.stream()))
+        return hv.reshape(x.shape), None, None, None, None, None, None
+
+
 class LogAbsSlaterDet(torch.autograd.Function):
-    """slater.py:4-60.  forward(orbitals, x): x (*batch, n, 2) -> log|det| (*batch)."""
+    """slater.py:4-60.  forward(orbitals, x): x (*batch, n, 2) -> log|det| (*batch).  Twice differentiable."""
 
     @staticmethod
     def forward(ctx, orbitals, x):
         orb = orbital_indices(orbitals, x.device)
         out, grad, _ = _run(x, orb, None, ctx.needs_input_grad[1])
-        ctx.save_for_backward(grad) if grad is not None else None
+        if grad is not None:
+            ctx.save_for_backward(x, grad)
+            ctx.orb = orb
         return out
 
     @staticmethod
     def backward(ctx, grad_logabsdet):
-        dlog, = ctx.saved_tensors
-        return None, grad_logabsdet[..., None, None] * dlog
+        x, dlog = ctx.saved_tensors
+        d = _SlaterGradient.apply(x, dlog, ctx.orb, None, x.shape[-2], 0, 1.0)
+        return None, grad_logabsdet[..., None, None] * d
 
 
 def logabsslaterdet(orbitals, x):                       # slater.py:62-68
@@ -77,13 +107,16 @@ class LogAbsSlaterDetMultStates(torch.autograd.Function):
         if ws.numel() != x.shape[0]:
             raise ValueError("batch must equal the sum of the multiplicities in state_indices_collection")
         out, grad, _ = _run(x, table, ws, ctx.needs_input_grad[2])
-        ctx.save_for_backward(grad) if grad is not None else None
+        if grad is not None:
+            ctx.save_for_backward(x, grad)
+            ctx.table, ctx.ws = table, ws
         return out
 
     @staticmethod
     def backward(ctx, grad_logabsdet):
-        dlog, = ctx.saved_tensors
-        return None, None, grad_logabsdet[:, None, None] * dlog
+        x, dlog = ctx.saved_tensors
+        d = _SlaterGradient.apply(x, dlog, ctx.table, ctx.ws, x.shape[-2], 0, 1.0)
+        return None, None, grad_logabsdet[:, None, None] * d
 
 
 def logabsslaterdetmultstates(states, state_indices_collection, x):   # slater.py:158-167

@@ -33,6 +33,17 @@ typedef struct ff_model {
 int ff_version(void);
 const char* ff_last_error(void);
 
+/* Kernel-variant switches for tests and A/B timing (no reference counterpart; the library never reads the
+ * environment).  Process-wide, thread-safe; 0 restores the default.  Names: no_table, no_w_balance, no_rt_cache,
+ * flow_warp_fill, flow_cta, flow_big, eloc_generic, slater_cta, metropolis_kernel (0 auto, 1 registers, 2 warp per
+ * walker, 3 thread per walker), adjoint_cta, pgrad_direct, pgrad_tile, pgrad_fixed_range.  Unknown name: -1. */
+/* Number of CUDA kernels this library has launched in the process so far (bench.py reports the difference over its
+ * timed region as "gpu_launches"). */
+long long ff_launch_count(void);
+
+int ff_set_option(const char* name, int value);
+int ff_get_option(const char* name, int* value);
+
 /* Backflow.forward / Backflow.divergence (equivariant_funs.py:80-102).
  * x [B][n][2] -> v [B][n][2] (nullable), div [B] (nullable). */
 int ff_backflow(const ff_model* m, const double* x, long long B, double* v, double* div, void* stream);
@@ -72,6 +83,13 @@ int ff_free_fermion_logp(const double* x, long long B, int n_up, int n_dn, const
  * Laplacian").  logp, grad, lap nullable. */
 int ff_free_fermion_logp_lap(const double* x, long long B, int n_up, int n_dn, const int* orb,
                              const int* walker_state, double* logp, double* grad, double* lap, void* stream);
+
+/* Double backward of LogAbsSlaterDet / LogAbsSlaterDetMultStates / FreeFermion.log_prob (slater.py:40-60 and
+ * 120-156 assemble the gradient from differentiable torch ops precisely so that utils.py:44-65 y_grad_laplacian can
+ * differentiate it again; reference tests/test_slater.py:65-127): hv = scale * Hessian(log|det Phi_up| +
+ * log|det Phi_dn|) v per walker, v and hv [B][n_up+n_dn][2].  One spin block: n_dn = 0. */
+int ff_slater_hvp(const double* x, long long B, int n_up, int n_dn, const int* orb, const int* walker_state,
+                  double scale, const double* v, double* hv, void* stream);
 
 /* FreeFermion.sample / sample_multstates (base_dist.py:58-70, 103-134): Metropolis chain of
  * `steps` whole-configuration moves x' = x + tau N(0,1), started from x ~ N(0,1).

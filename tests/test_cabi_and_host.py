@@ -102,3 +102,85 @@ def test_vmc_rejects_unsupported_potentials():
     cnf = CNF(Backflow(MLP(1, 4)), (0.0, 1.0))
     with pytest.raises(NotImplementedError):
         GSVMC(2, 0, HO2D(), FreeFermion("cpu"), cnf, Other())
+
+
+REFERENCE_CNF_KEYS = [   # list(CNF(Backflow(MLP(1, H), mu=MLP(1, H)), t_span).state_dict()) of reference src/flow.py:28,37
+    "v_wrapper.v.eta.fc1.weight", "v_wrapper.v.eta.fc1.bias", "v_wrapper.v.eta.fc2.weight",
+    "v_wrapper.v.mu.fc1.weight", "v_wrapper.v.mu.fc1.bias", "v_wrapper.v.mu.fc2.weight",
+    "f.v.eta.fc1.weight", "f.v.eta.fc1.bias", "f.v.eta.fc2.weight",
+    "f.v.mu.fc1.weight", "f.v.mu.fc1.bias", "f.v.mu.fc2.weight"]
+
+
+def test_cnf_state_dict_has_the_reference_layout():
+    """A checkpoint of the reference's CNF / GSVMC loads with strict=True and vice versa (flow.py:18-37)."""
+    from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
+    cnf = CNF(Backflow(MLP(1, 4), mu=MLP(1, 3)), (0.0, 1.0))
+    assert list(cnf.state_dict()) == REFERENCE_CNF_KEYS
+    assert len(list(cnf.parameters())) == 6                           # shared parameters are not duplicated
+    ref_ckpt = {k: torch.randn_like(v) for k, v in cnf.state_dict().items()}
+    for k in list(ref_ckpt):                                          # the reference stores the same tensor twice
+        if k.startswith("f.v."):
+            ref_ckpt[k] = ref_ckpt["v_wrapper.v." + k[4:]]
+    cnf.load_state_dict(ref_ckpt, strict=True)
+    assert torch.equal(cnf.v.eta.fc1.weight, ref_ckpt["v_wrapper.v.eta.fc1.weight"])
+    assert cnf.v is cnf.v_wrapper.v and cnf.v is cnf.f.v
+    model = GSVMC(2, 1, HO2D(), FreeFermion("cpu"), cnf, CoulombPairPotential(2.0), sp_potential=HO())
+    assert list(model.state_dict()) == ["cnf." + k for k in REFERENCE_CNF_KEYS]
+    # checkpoints written by round-1 builds (`v.eta...`) are remapped
+    old = {"v." + k[len("v_wrapper.v."):]: torch.randn_like(v) for k, v in cnf.state_dict().items() if k.startswith("v_wrapper")}
+    cnf.load_state_dict(old, strict=True)
+    assert torch.equal(cnf.v.mu.fc2.weight, old["v.mu.fc2.weight"])
+
+
+def test_reference_cnf_checkpoint_round_trip_if_reference_present():
+    """With /root/reference available (build container only): save from the real reference, load here, and back."""
+    import sys
+    ref = os.environ.get("FERMIFLOW_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "src")):
+        pytest.skip("reference sources not present on this machine")
+    import subprocess
+    code = (
+        "import sys, torch\n"
+        "sys.path[:0] = [%r, %r]\n"
+        "from MLP import MLP; from equivariant_funs import Backflow; from flow import CNF\n"
+        "c = CNF(Backflow(MLP(1, 5), mu=MLP(1, 4)), (0., 1.))\n"
+        "torch.save(c.state_dict(), sys.argv[1])\n"
+        "if len(sys.argv) > 2: c.load_state_dict(torch.load(sys.argv[2]), strict=True); print('loaded-ours')\n"
+    ) % (os.path.join(ROOT, "oracle", "torchdiffeq_shim"), os.path.join(ref, "src"))
+    import tempfile
+    from fermiflow_b200 import MLP, Backflow, CNF
+    with tempfile.TemporaryDirectory() as d:
+        a, b = os.path.join(d, "ref.pt"), os.path.join(d, "ours.pt")
+        subprocess.run([sys.executable, "-W", "ignore", "-c", code, a], check=True)
+        cnf = CNF(Backflow(MLP(1, 5), mu=MLP(1, 4)), (0.0, 1.0))
+        cnf.load_state_dict(torch.load(a), strict=True)
+        torch.save(cnf.state_dict(), b)
+        out = subprocess.run([sys.executable, "-W", "ignore", "-c", code, a, b], check=True, capture_output=True, text=True)
+        assert "loaded-ours" in out.stdout
+
+
+def test_metropolis_seed_and_rank_offset(monkeypatch):
+    """FreeFermion draws its default seed from torch's generator and offsets the Philox walker index by rank * B
+    (every rank gets its own chains)."""
+    from fermiflow_b200 import base_dist as BD
+    calls = []
+
+    class FakeLib:
+        def ff_metropolis(self, B, n_up, n_dn, orb, ws, steps, tau, seed, offset, *rest):
+            calls.append((B, seed, offset))
+            return 0
+    monkeypatch.setattr(BD.L, "lib", lambda: FakeLib())
+    monkeypatch.setattr(BD.L, "ptr", lambda t, dtype=None: None)
+    monkeypatch.setattr(BD.L, "stream", lambda: None)
+    monkeypatch.setattr(BD, "orbital_indices", lambda orbs, dev: None)
+    torch.manual_seed(123)
+    fd = BD.FreeFermion("cpu")
+    fd.sample((0, 1), (0,), (8,))
+    fd.sample((0, 1), (0,), (8,))
+    assert calls[0][1] == 123 and calls[1][1] != calls[0][1] and calls[0][2] == 0
+    monkeypatch.setattr(BD, "_rank_world", lambda: (3, 4))
+    fd.manual_seed(7)
+    fd.sample((0, 1), (0,), (8,))
+    assert calls[2] == (8, 7, 24)
+    torch.manual_seed(124)
+    assert BD.FreeFermion("cpu").seed is None

@@ -429,25 +429,22 @@ def test_flow_reversibility_full_size(dev):
 # ---------------------------------------------------------------------------------------
 # Kernel variants: every specialised kernel must agree with the oracle / the generic kernel.
 
-def _env(**kw):
-    import contextlib, os
+def _opts(**kw):
+    """Kernel-variant switches of the library (ff_set_option), restored on exit; stash_radial is the Python-side one."""
+    import contextlib
+    from fermiflow_b200 import _lib as L
 
     @contextlib.contextmanager
     def cm():
-        old = {k: os.environ.get(k) for k in kw}
+        stash = kw.pop("stash_radial", None)
+        old_stash = L.STASH_RADIAL
         try:
-            for k, v in kw.items():
-                if v is None:
-                    os.environ.pop(k, None)
-                else:
-                    os.environ[k] = v
-            yield
+            if stash is not None:
+                L.STASH_RADIAL = bool(stash)
+            with L.options(**kw):
+                yield
         finally:
-            for k, v in old.items():
-                if v is None:
-                    os.environ.pop(k, None)
-                else:
-                    os.environ[k] = v
+            L.STASH_RADIAL = old_stash
     return cm()
 
 
@@ -495,14 +492,13 @@ def _n20_model(dev, nsteps=8, H=50):
 
 
 def test_flow_kernel_variants_agree_full_size(dev):
-    """N = 20: one-warp-per-walker sweeps against the CTA-synchronous flow_kernel (FF_FLOW_CTA=1)
-    and its 128-register build (FF_FLOW_BIG=1) on the same walkers."""
+    """N = 20: one-warp-per-walker sweeps against the CTA-synchronous flow_kernel (option flow_cta)
+    and its 128-register build (flow_big) on the same walkers."""
     model = _n20_model(dev)
     z, _ = model.sample((777,))
     outs = []
-    for env in (dict(FF_FLOW_CTA=None, FF_FLOW_BIG=None), dict(FF_FLOW_CTA="1", FF_FLOW_BIG=None),
-                dict(FF_FLOW_CTA="1", FF_FLOW_BIG="1")):
-        with _env(**env):
+    for env in (dict(flow_cta=0, flow_big=0), dict(flow_cta=1, flow_big=0), dict(flow_cta=1, flow_big=1)):
+        with _opts(**env):
             x = model.cnf.generate(z)
             zz, dl = model.cnf.delta_logp(x)
             outs.append((x, zz, dl))
@@ -514,16 +510,14 @@ def test_flow_kernel_variants_agree_full_size(dev):
 
 @pytest.mark.parametrize("B", [1, 2, 297, 1500])
 def test_eloc_kernel_variants_agree_full_size(dev, B):
-    """N = 20: the statically specialised sweep (default), the generic flow_kernel<MODE_ELOC>
-    (FF_NO_STATIC=1, the one pinned against the oracle at small N), the warp-specialised
-    two-walker pipeline (FF_ELOC_V3=1; odd walker counts exercise its slot shutdown) and the
-    barrier-synchronous kernel with fused phases (FF_ELOC_V2=1)."""
+    """N = 20: the statically specialised sweep (default) against the generic flow_kernel<MODE_ELOC>
+    (option eloc_generic), with the Taylor tables and with direct evaluation of every hidden unit (no_table)."""
     model = _n20_model(dev, nsteps=4)
     _, x = model.sample((B,))
     res = []
-    for env in (dict(FF_NO_STATIC=None, FF_ELOC_V3=None, FF_ELOC_V2=None), dict(FF_NO_STATIC="1", FF_ELOC_V3=None, FF_ELOC_V2=None),
-                dict(FF_NO_STATIC=None, FF_ELOC_V3="1", FF_ELOC_V2=None), dict(FF_NO_STATIC=None, FF_ELOC_V3=None, FF_ELOC_V2="1")):
-        with _env(**env):
+    for env in (dict(eloc_generic=0, no_table=0), dict(eloc_generic=1, no_table=0), dict(eloc_generic=0, no_table=1),
+                dict(eloc_generic=1, no_table=1)):
+        with _opts(**env):
             res.append(model.local_energy(x, stash=True))
     for r in res[1:]:
         for k in ("z", "logp", "grad", "lap", "kinetic", "potential", "eloc"):
@@ -536,14 +530,14 @@ def test_eloc_kernel_variants_agree_full_size(dev, B):
 def test_free_fermion_logp_grad_laplacian_vs_oracle(dev, O, nup, ndn):
     """BASELINE.json config "batched log|det| + exact Laplacian": the fused kernel (one warp per
     walker) against the reference's way -- 1 + 2N autograd passes through FreeFermion.log_prob
-    (utils.py:44-65) -- and against the CTA-cooperative kernel (FF_SLATER_CTA=1)."""
+    (utils.py:44-65) -- and against the CTA-cooperative kernel (option slater_cta)."""
     from fermiflow_b200 import HO2D, FreeFermion
     ho, ff = HO2D(), FreeFermion(dev)
     n = nup + ndn
     gen = torch.Generator().manual_seed(100 + n)
     x = 1.1 * torch.randn(40, n, 2, generator=gen)
     lp, g, lap = ff.log_prob_grad_laplacian(ho.orbitals[:nup], ho.orbitals[:ndn], x.to(dev))
-    with _env(FF_SLATER_CTA="1"):
+    with _opts(slater_cta=1):
         lp2, g2, lap2 = ff.log_prob_grad_laplacian(ho.orbitals[:nup], ho.orbitals[:ndn], x.to(dev))
     rlp, rg, rlap = O.free_fermion_grad_laplacian(list(range(nup)), list(range(ndn)), x)
     # conditioning of the random 15 x 15 Slater matrices limits the agreement at N = 30
@@ -559,9 +553,8 @@ def test_metropolis_kernels_bit_identical(dev, nup, ndn):
     from fermiflow_b200 import HO2D, FreeFermion
     ho = HO2D()
     outs = []
-    for env in (dict(FF_METRO_THREAD=None, FF_METRO_REG=None), dict(FF_METRO_THREAD="1", FF_METRO_REG=None),
-                dict(FF_METRO_THREAD=None, FF_METRO_REG="1")):
-        with _env(**env):
+    for env in (dict(metropolis_kernel=2), dict(metropolis_kernel=3), dict(metropolis_kernel=1)):
+        with _opts(**env):
             ff = FreeFermion(dev)
             ff.manual_seed(77)
             outs.append(ff.sample(ho.orbitals[:nup], ho.orbitals[:ndn], (1000,), equilibrim_steps=40))
@@ -576,8 +569,8 @@ def test_metropolis_register_kernel_default_at_bench_size(dev):
     from fermiflow_b200 import HO2D, FreeFermion
     ho = HO2D()
     outs = []
-    for env in (dict(FF_METRO_WARP=None), dict(FF_METRO_WARP="1")):
-        with _env(**env):
+    for env in (dict(metropolis_kernel=0), dict(metropolis_kernel=2)):
+        with _opts(**env):
             ff = FreeFermion(dev)
             ff.manual_seed(5)
             outs.append(ff.sample(ho.orbitals[:10], ho.orbitals[:10], (8192 + 77,), equilibrim_steps=100))
@@ -587,8 +580,8 @@ def test_metropolis_register_kernel_default_at_bench_size(dev):
               for up, dn in (([0, 1, 2, 3], [0, 1]), ([0, 2, 7, 20], [1, 27]), ([1, 5, 9, 14], [3, 35]))]
     sidx = (torch.arange(9000) % 3).to(torch.int32).to(dev)
     outs = []
-    for env in (dict(FF_METRO_WARP=None), dict(FF_METRO_WARP="1")):
-        with _env(**env):
+    for env in (dict(metropolis_kernel=0), dict(metropolis_kernel=2)):
+        with _opts(**env):
             ff = FreeFermion(dev)
             ff.manual_seed(6)
             outs.append(ff.sample_multstates(states, sidx, (9000,), equilibrim_steps=30))
@@ -604,7 +597,7 @@ def test_metropolis_register_kernel_replay_vs_oracle(dev, O):
     nrm = torch.randn(steps, B, nup + ndn, 2, generator=gen)
     uni = torch.rand(steps, B, generator=gen)
     ref = O.metropolis_sample(list(range(nup)), list(range(ndn)), x0, nrm, uni, tau=0.1)
-    with _env(FF_METRO_REG="1"):
+    with _opts(metropolis_kernel=1):
         x = FreeFermion(dev).sample(ho.orbitals[:nup], ho.orbitals[:ndn], (B,), equilibrim_steps=steps,
                                     noise=(x0.to(dev), nrm.to(dev), uni.to(dev)))
     close(x, ref, 1e-13)
@@ -623,7 +616,7 @@ def _sweeps(model, z):
 @pytest.mark.parametrize("case", ["bench", "sharp", "too_sharp", "zero", "far"])
 def test_radial_tables_match_direct_evaluation(dev, case):
     """Every sweep with the certified Taylor tables (default) against the direct sum over hidden units
-    (FF_NO_TABLE=1).  sharp: max|w1| = 12 (0.008 node spacing); too_sharp: max|w1| = 60, the table does not
+    (option no_table).  sharp: max|w1| = 12 (0.008 node spacing); too_sharp: max|w1| = 60, the table does not
     fit and every lane falls back; zero: all-zero MLPs; far: walkers beyond the tabulated range (d > 24)."""
     from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
     gen = torch.Generator().manual_seed(31)
@@ -644,7 +637,7 @@ def test_radial_tables_match_direct_evaluation(dev, case):
     z = model.basedist.sample(model.orbitals_up, model.orbitals_down, (300,))
     if case == "far":
         z = z.clone(); z[::7, 3, 0] += 27.0          # one particle outside the table range (pair distances > 24)
-    with _env(FF_NO_TABLE="1"):
+    with _opts(no_table=1):
         ref = _sweeps(model, z)
     got = _sweeps(model, z)
     for k in ref:
@@ -655,7 +648,7 @@ def test_radial_tables_match_direct_evaluation(dev, case):
 @pytest.mark.parametrize("case", ["bench", "sharp", "too_sharp", "zero", "far", "far_few", "no_mu"])
 def test_binned_parameter_gradient_matches_direct(dev, case):
     """ff_logp_backward through binned Taylor moments (default) against the direct kernel that evaluates every
-    hidden unit per record (FF_NO_BINNED_PGRAD=1).  sharp: max|w1| = 3 (bins just fit); too_sharp: max|w1| = 40,
+    hidden unit per record (option pgrad_direct).  sharp: max|w1| = 3 (bins just fit); too_sharp: max|w1| = 40,
     the bins do not fit and the device-side flag hands the work to the direct kernel; far: 3.6 % of the pair records
     beyond d = 24, more than the tail the in-kernel direct path is meant for -> the device-side flag selects the
     direct kernel; far_few: 0.2 % beyond the node range, summed directly inside the binned kernel; zero: all-zero
@@ -690,7 +683,7 @@ def test_binned_parameter_gradient_matches_direct(dev, case):
         lp = model.logp(x, params_require_grad=True)
         (lp * w).sum().backward()
         return [p.grad.clone() for p in model.parameters()]
-    with _env(FF_NO_BINNED_PGRAD="1"):
+    with _opts(pgrad_direct=1):
         ref = grads()
     got = grads()
     for a, b in zip(got, ref):
@@ -701,7 +694,7 @@ def test_binned_parameter_gradient_matches_direct(dev, case):
 @pytest.mark.parametrize("case", ["bench", "far", "too_sharp"])
 def test_backward_with_and_without_radial_stash(dev, case):
     """ff_logp_backward reads the (f, f', f'') stash the forward sweep wrote (22 GB per 65536 walkers at n = 20);
-    with FF_NO_STASH_C=1 it recomputes them from the stage inputs.  Both must give the same gradients (far: distances
+    with _lib.STASH_RADIAL = False it recomputes them from the stage inputs.  Both must give the same gradients (far: distances
     outside the Taylor table, too_sharp: no usable table -> direct sums in the adjoint sweep)."""
     from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
     gen = torch.Generator().manual_seed(91)
@@ -730,7 +723,7 @@ def test_backward_with_and_without_radial_stash(dev, case):
         (lp * w).sum().backward()
         return [xr.grad.clone()] + [p.grad.clone() for p in model.parameters()]
     ref = grads()
-    with _env(FF_NO_STASH_C="1"):
+    with _opts(stash_radial=False):
         got = grads()
     for a, b in zip(got, ref):
         assert torch.isfinite(a).all()
@@ -740,7 +733,7 @@ def test_backward_with_and_without_radial_stash(dev, case):
 @pytest.mark.parametrize("nup,ndn,Hm,stash_c", [(10, 10, 16, True), (10, 10, 16, False), (3, 2, 0, True), (6, 6, 8, True)])
 def test_adjoint_warp_kernel_matches_cta_kernel(dev, nup, ndn, Hm, stash_c):
     """The one-warp-per-walker reverse sweep (default) performs the arithmetic of the CTA-synchronous kernel
-    (FF_ADJ_CTA=1) in the same order: d log p / dx is bit-identical, with and without the (f, f', f'') stash."""
+    (option adjoint_cta) in the same order: d log p / dx is bit-identical, with and without the (f, f', f'') stash."""
     from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
     gen = torch.Generator().manual_seed(17)
     H = 16
@@ -763,10 +756,10 @@ def test_adjoint_warp_kernel_matches_cta_kernel(dev, nup, ndn, Hm, stash_c):
         xr = x.clone().requires_grad_(True)
         (model.logp(xr, params_require_grad=True) * w).sum().backward()
         return xr.grad.clone()
-    env = {} if stash_c else dict(FF_NO_STASH_C="1")
-    with _env(FF_ADJ_CTA=None, **env):
+    env = {} if stash_c else dict(stash_radial=False)
+    with _opts(adjoint_cta=0, **env):
         g_warp = grad_x()
-    with _env(FF_ADJ_CTA="1", **env):
+    with _opts(adjoint_cta=1, **env):
         g_cta = grad_x()
     assert torch.isfinite(g_warp).all()
     assert torch.equal(g_warp, g_cta)
@@ -799,15 +792,131 @@ def test_generate_trajectory_frames_and_reversibility_check(dev, O):
 def test_eloc_static_kernel_spin_polarised_many_walkers_per_cta(dev):
     """Spin-polarised N = 12 (BASELINE config 3): the statically specialised sweep keeps its finale scratch partly
     in the dead J1 buffer and re-zeroes it; with ~7 walkers per CTA it must agree with the generic kernel
-    (FF_ELOC_V1=1 FF_NO_STATIC=1), walker by walker."""
+    (option eloc_generic), walker by walker."""
     from fermiflow_b200 import Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
     cnf = CNF(Backflow(rand_mlp(20, 5, 0.03, dev), mu=rand_mlp(20, 6, 0.03, dev)), (0.0, 1.0), nsteps=3)
     model = GSVMC(12, 0, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(8.0), sp_potential=HO()).to(dev)
     _, x = model.sample((2101,))
-    with _env(FF_ELOC_V1=None, FF_NO_STATIC=None):
+    with _opts(eloc_generic=0):
         r0 = model.local_energy(x, stash=True)
-    with _env(FF_ELOC_V1="1", FF_NO_STATIC="1"):
+    with _opts(eloc_generic=1):
         r1 = model.local_energy(x, stash=True)
     for k in ("z", "logp", "grad", "lap", "kinetic", "potential", "eloc"):
         close(getattr(r1, k), getattr(r0, k), 1e-10, 1e-11)
     close(r1.stash.y, r0.stash.y, 1e-13)
+
+
+# ---- higher-order differentiability of the Slater primitives (reference tests/test_slater.py:65-127) ----------------
+def _direct_logabsdet(orb_idx, x, O):
+    """slater.py:62-68 logabsslaterdet: torch.slogdet of the orbital matrix, differentiated by plain autograd."""
+    return O.logabs_slater(orb_idx, x)
+
+
+def test_LogAbsSlaterDet_twice_differentiable(dev, O):
+    """Port of the reference's "IMPORTANT TEST" (tests/test_slater.py:65-92): y_grad_laplacian through the custom
+    primitive (backward = Jacobi-formula kernel, double backward = Hessian-vector-product kernel) against plain
+    autograd through slogdet."""
+    import random
+    from fermiflow_b200 import HO2D
+    from fermiflow_b200.slater import LogAbsSlaterDet
+    from fermiflow_b200.utils import y_grad_laplacian
+    ho = HO2D()
+    random.seed(4)
+    for n, batch in ((3, 20), (10, 7), (20, 3)):
+        orbitals, _ = ho.fermion_states_random(n)
+        idx = [o.index for o in orbitals]
+        x = torch.randn(batch, n, 2, generator=torch.Generator().manual_seed(n))
+        xg = x.to(dev).requires_grad_(True)
+        y, gy, ly = y_grad_laplacian(lambda t: LogAbsSlaterDet.apply(orbitals, t), xg)
+        assert y.shape == (batch,) and gy.shape == (batch, n, 2) and ly.shape == (batch,)
+        xc = x.clone().requires_grad_(True)
+        xf = xc.flatten(1)
+        yd = _direct_logabsdet(idx, xf.view_as(xc), O)
+        gd, = torch.autograd.grad(yd.sum(), xf, create_graph=True)
+        ld = sum(torch.autograd.grad(gd[:, i].sum(), xf, retain_graph=True)[0][:, i] for i in range(2 * n))
+        close(y, yd)
+        close(gy, gd.view_as(xc), 1e-9)
+        close(ly, ld, 1e-8)
+        # a full Hessian-vector product, not only its diagonal
+        v = torch.randn(batch, n, 2, generator=torch.Generator().manual_seed(100 + n))
+        out = LogAbsSlaterDet.apply(orbitals, xg)
+        g1, = torch.autograd.grad(out.sum(), xg, create_graph=True)
+        hv, = torch.autograd.grad((g1 * v.to(dev)).sum(), xg)
+        hvd, = torch.autograd.grad((gd.view_as(xc) * v).sum(), xc)
+        close(hv, hvd, 1e-8)
+        # agrees with the fused single-launch Laplacian
+        from fermiflow_b200.slater import slater_value_grad_laplacian
+        close(slater_value_grad_laplacian(orbitals, xg.detach())[2], ly, 1e-9)
+
+
+def test_LogAbsSlaterDetMultStates_twice_differentiable(dev, O):
+    """Port of reference tests/test_slater.py:94-127."""
+    import random
+    from fermiflow_b200 import HO2D, FreeFermion
+    from fermiflow_b200.slater import LogAbsSlaterDetMultStates
+    from fermiflow_b200.utils import y_grad_laplacian
+    ho = HO2D()
+    random.seed(8)
+    n, Nstates = 5, 10
+    states = tuple(ho.fermion_states_random(n)[0] for _ in range(Nstates))
+    coll = dict(zip(range(Nstates), random.choices(range(2, 6), k=Nstates)))
+    batch = sum(coll.values())
+    x = torch.randn(batch, n, 2, generator=torch.Generator().manual_seed(3))
+    xg = x.to(dev).requires_grad_(True)
+    y, gy, ly = y_grad_laplacian(lambda t: LogAbsSlaterDetMultStates.apply(states, coll, t), xg)
+    occ = torch.tensor([[o.index for o in states[k]] for k, times in coll.items() for _ in range(times)])
+    xc = x.clone().requires_grad_(True)
+    xf = xc.flatten(1)
+    yd = O.logabs_slater(occ, xf.view_as(xc))
+    gd, = torch.autograd.grad(yd.sum(), xf, create_graph=True)
+    ld = sum(torch.autograd.grad(gd[:, i].sum(), xf, retain_graph=True)[0][:, i] for i in range(2 * n))
+    close(y, yd)
+    close(gy, gd.view_as(xc), 1e-9)
+    close(ly, ld, 1e-8)
+    # FreeFermion.log_prob (two spin blocks, scale 2) through the generic loop and through the fused fast path
+    fd = FreeFermion(dev)
+    up, dn = ho.orbitals[:3], ho.orbitals[:2]
+    x5 = torch.randn(9, 5, 2, generator=torch.Generator().manual_seed(5)).to(dev).requires_grad_(True)
+    ya, ga, la = y_grad_laplacian(lambda t: fd.log_prob(up, dn, t), x5)
+    import functools
+    yb, gb, lb = y_grad_laplacian(functools.partial(fd.log_prob, up, dn), x5)
+    close(ya, yb, 1e-13); close(ga, gb, 1e-12); close(la, lb, 1e-10)
+    ref = O.free_fermion_grad_laplacian([0, 1, 2], [0, 1], x5.detach().cpu())
+    close(la, ref[2], 1e-9)
+
+
+def test_y_grad_laplacian_generic_and_vmc_dispatch(dev, O):
+    """reference tests/test_utils.py:37 (a polynomial through the generic autograd loop) and the dispatch of a bound
+    GSVMC.logp to the forward-mode sweep."""
+    from fermiflow_b200 import Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
+    from fermiflow_b200.utils import y_grad_laplacian
+    batch, n, dim = 10, 5, 3
+    w = torch.randn(batch, n, dim, device=dev)
+    f = lambda t: ((t ** 3 + 5 * t ** 2) * w).sum(dim=(-2, -1))
+    x = torch.randn(batch, n, dim, device=dev, requires_grad=True)
+    y, gy, ly = y_grad_laplacian(f, x)
+    close(y, f(x), 1e-13)
+    close(gy, (3 * x ** 2 + 10 * x) * w, 1e-13)
+    close(ly, ((6 * x + 10) * w).sum(dim=(-2, -1)), 1e-12)
+    eta, mu = rand_mlp(8, 1, 0.05, dev), rand_mlp(6, 2, 0.05, dev)
+    cnf = CNF(Backflow(eta, mu=mu), (0.0, 1.0), nsteps=8)
+    model = GSVMC(3, 2, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(2.0), sp_potential=HO()).to(dev)
+    xs = 0.9 * torch.randn(4, 5, 2, generator=torch.Generator().manual_seed(2))
+    lp, g, lap = y_grad_laplacian(model.logp, xs.to(dev))
+    ref = O.logp_grad_laplacian(xs, [0, 1, 2], [0, 1], cpu_params(eta), cpu_params(mu), (0.0, 1.0), 8)
+    close(lp, ref[0]); close(g, ref[1]); close(lap, ref[2])
+    # the flow's own backward is first order only and says so
+    xr = xs.to(dev).requires_grad_(True)
+    gx, = torch.autograd.grad(model.logp(xr).sum(), xr, create_graph=True)
+    with pytest.raises(RuntimeError):
+        torch.autograd.grad(gx.sum(), xr)
+
+
+def test_default_seeding_follows_torch_and_differs_between_calls(dev):
+    from fermiflow_b200 import HO2D, FreeFermion
+    ho = HO2D()
+    torch.manual_seed(11); a = FreeFermion(dev).sample(ho.orbitals[:3], ho.orbitals[:2], (64,))
+    torch.manual_seed(11); fd = FreeFermion(dev); b = fd.sample(ho.orbitals[:3], ho.orbitals[:2], (64,))
+    c = fd.sample(ho.orbitals[:3], ho.orbitals[:2], (64,))
+    torch.manual_seed(12); d = FreeFermion(dev).sample(ho.orbitals[:3], ho.orbitals[:2], (64,))
+    assert torch.equal(a, b) and not torch.equal(b, c) and not torch.equal(a, d)
