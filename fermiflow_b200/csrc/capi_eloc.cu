@@ -1,0 +1,78 @@
+// C ABI, E_loc sweep (ff_eloc): statically specialised kernels for the particle numbers of the BASELINE.json configs,
+// generic flow_kernel<MODE_ELOC> otherwise.  Separate translation unit (the kernels dominate the build time).
+#include "capi_flow.h"
+#include "ff_eloc2.cuh"
+
+using namespace ffc;
+
+namespace {
+
+// Barrier-synchronous sweep with fused phases (ff_eloc2.cuh eloc2_kernel).
+template <int SN, int SMU>
+int launch_eloc2(ff::FlowArgs& a, cudaStream_t st) {
+    constexpr ff::Eloc2Geom g = ff::eloc2_geom(SN, SMU != 0);
+    constexpr ff::Eloc2Launch q = ff::eloc2_launch(SN, SMU != 0);
+    a.D = g.D; a.NP = g.NP; a.P = g.P; a.DP = g.DP; a.NV = g.NV; a.NSV = g.NSV; a.grec = ff::kGRec;
+    a.off_G = g.off_G; a.off_AM = g.off_AM; a.off_u = g.off_u; a.off_kLx = g.off_kLx; a.off_part = g.off_part;
+    a.off_x0 = g.off_x0; a.off_sl = g.off_sl; a.wstride = g.wstride; a.W = 1;
+    const int need = ff::slater_scratch_size(a.n_up, a.n - a.n_up) + 2 * g.D + g.n * g.n + g.NP + 8;
+    // finale scratch: the two RK partial buffers plus J1 (dead after the last stage; eloc2_kernel re-zeroes it)
+    if (need > 3 * g.MAT) return FF_FALLBACK;  // the generic kernel takes over
+    constexpr int NI = FF_ELOC2_ILP;
+    const int common = ff::kTabDoubles + 6 * (ff::coef_rows2<NI>(a.H_eta) + ff::coef_rows2<NI>(a.H_mu)) + 2 * ((g.NP + 7) / 8) + 2;
+    size_t smem = (size_t)(common + g.wstride) * 8;
+    if ((long long)smem > dev_info().smem_optin) return FF_FALLBACK;
+    {   // what is left of this CTA's share of the SM mirrors the head of the eta table (96 bytes per node)
+        const DevInfo di = dev_info();
+        // ... without lowering the number of resident CTAs the register allocation aims at
+        const int occ = ff::eloc2_min_blocks(q.threads);
+        const long long share = (long long)di.smem_sm / occ - di.smem_reserved - 64;
+        const long long room = std::min<long long>(share, di.smem_optin) - (long long)smem;
+        a.rt_cache_nodes = (a.rt_eta != nullptr && room > 0) ? (int)std::min<long long>(room / (8 * ff::kRtCoef), 2048) : 0;
+        smem += (size_t)a.rt_cache_nodes * 8 * ff::kRtCoef;
+    }
+    return launch_flow_kernel(ff::eloc2_kernel<SN, SMU>, a, q.threads, smem, st);
+}
+
+// Statically specialised E_loc sweeps (ff_eloc2.cuh) for the particle numbers of the BASELINE.json configs; anything
+// else, or "eloc_generic", runs the generic flow_kernel<MODE_ELOC>.
+int try_eloc_static(ff::FlowArgs& a, cudaStream_t st) {
+    if (opt(OPT_ELOC_GENERIC) || a.H_mu <= 0) return FF_FALLBACK;
+    switch (a.n) {
+        case 20: return launch_eloc2<20, 1>(a, st);
+        case 12: return launch_eloc2<12, 1>(a, st);
+        case 6: return launch_eloc2<6, 1>(a, st);
+        default: return FF_FALLBACK;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ff_eloc(const ff_model* m, const double* x, long long B, const int* orb, const int* walker_state,
+            double Z, int harmonic, double* z, double* delta_logp, double* logp, double* grad,
+            double* lap, double* kinetic, double* potential, double* eloc,
+            double* stash_y, double* stash_c, void* stream) {
+    if (int e = check_model(m)) return e;
+    if (B < 0 || (B > 0 && (!x || !orb))) return fail(-1, "ff_eloc: null input");
+    if (stash_c && !stash_y) return fail(-1, "ff_eloc: stash_c needs stash_y");
+    ff::FlowArgs a{};
+    int threads; size_t smem;
+    if (int e = plan_flow(ff::MODE_ELOC, m, a, threads, smem)) return e;
+    a.ta = m->t1; a.tb = m->t0;
+    a.B = B; a.x_in = x; a.y_out = z; a.delta_out = delta_logp;
+    a.stash_y = stash_y; a.stash_c = stash_c;
+    a.orb = orb; a.walker_state = walker_state; a.Z = Z; a.harmonic = harmonic;
+    a.logp = logp; a.grad = grad; a.lap = lap; a.kin = kinetic; a.pot = potential; a.eloc = eloc;
+    RadialTables rt;
+    if (int e = rt.build(m, (cudaStream_t)stream, a)) return e;
+    {
+        ff::FlowArgs a2 = a;
+        const int r = try_eloc_static(a2, (cudaStream_t)stream);
+        if (r != FF_FALLBACK) return r;
+    }
+    return launch_flow<ff::MODE_ELOC>(a, threads, smem, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -12,7 +12,7 @@ constexpr int kGRec = 11;        // per-item gather record length (odd: bank-con
 // keeps a shared-memory copy replicated 16 times (entry j of lane l at tab[16 j + (l & 15)]),
 // so that the per-lane table look-up of the exponential is bank-conflict free.
 constexpr int kTabDoubles = 512;
-__constant__ double c_exp2_32[32] = {
+static __constant__ double c_exp2_32[32] = {
     1.0,
     1.0218971486541166,
     1.0442737824274138,
@@ -55,7 +55,7 @@ __device__ __forceinline__ void fill_exp_table(double* tab) {
 // [3..6]: degree-5 polynomial of exp(r) on |r| <= ln2/64 -- the degree-6 Taylor polynomial with its
 // r^6 term economised onto Chebyshev T6 (max relative error 1.4e-16):
 //   exp(r) ~ 1 + r + c2 r^2 + r^3/6 + c4 r^4 + r^5/120,  c2 = 1/2 - a^4/1280,  c4 = 1/24 + a^2/480.
-__constant__ double c_sig[8] = {46.16624130844683,        // 32 / ln 2
+static __constant__ double c_sig[8] = {46.16624130844683,        // 32 / ln 2
                                 0.02166084938653512,      // ln2/32, low 21 mantissa bits zero
                                 5.9631716539705866e-12,   // ln2/32 remainder
                                 1.0 / 120.0, 0.04166691103770646, 1.0 / 6.0, 0.4999999999892509, 0.0};
@@ -244,9 +244,9 @@ __device__ __forceinline__ void hermite_values(double x, double (&v)[8]) {
     }
 }
 
-__constant__ unsigned char c_orb_nx[kMaxOrb] = {
+static __constant__ unsigned char c_orb_nx[kMaxOrb] = {
     0, 0,1, 0,1,2, 0,1,2,3, 0,1,2,3,4, 0,1,2,3,4,5, 0,1,2,3,4,5,6, 0,1,2,3,4,5,6,7};
-__constant__ unsigned char c_orb_ny[kMaxOrb] = {
+static __constant__ unsigned char c_orb_ny[kMaxOrb] = {
     0, 1,0, 2,1,0, 3,2,1,0, 4,3,2,1,0, 5,4,3,2,1,0, 6,5,4,3,2,1,0, 7,6,5,4,3,2,1,0};
 
 // D(8x8) += A(8x4) * B(4x8) on the FP64 tensor cores (DMMA).  Lane l holds A[l/4][l%4],

@@ -15,7 +15,7 @@
 namespace ff {
 
 #ifdef FF_PHASE_TIMING
-__device__ unsigned long long g_phase_cycles[16];
+static __device__ unsigned long long g_phase_cycles[16];
 #define FF_TICK(k) do { if (MODE == MODE_ELOC && tid == 0) { long long now_ = clock64(); tacc[k] += now_ - tlast; tlast = now_; } } while (0)
 #else
 #define FF_TICK(k) do {} while (0)

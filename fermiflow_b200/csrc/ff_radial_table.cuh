@@ -29,7 +29,7 @@ constexpr double kRtMaxDelta = 0.125;
 __host__ __device__ constexpr size_t radial_table_doubles() { return kRtHeader + (size_t)kRtMaxNodes * kRtCoef; }
 
 // P_m(s), m = 0..11, lowest power first; P_m starts at c_sigpoly_off[m] and has m + 2 coefficients
-__constant__ double c_sigpoly[90] = {
+static __constant__ double c_sigpoly[90] = {
     0.0, 1.0, 0.0, 1.0, -1.0, 0.0, 1.0, -3.0, 2.0, 0.0, 1.0, -7.0, 12.0, -6.0, 0.0, 1.0, -15.0, 50.0, -60.0,
     24.0, 0.0, 1.0, -31.0, 180.0, -390.0, 360.0, -120.0, 0.0, 1.0, -63.0, 602.0, -2100.0, 3360.0, -2520.0,
     720.0, 0.0, 1.0, -127.0, 1932.0, -10206.0, 25200.0, -31920.0, 20160.0, -5040.0, 0.0, 1.0, -255.0, 6050.0,
@@ -38,8 +38,8 @@ __constant__ double c_sigpoly[90] = {
     -21538440.0, 46070640.0, -59875200.0, 46569600.0, -19958400.0, 3628800.0, 0.0, 1.0, -2047.0, 173052.0,
     -3669006.0, 33105600.0, -158838240.0, 451725120.0, -801496080.0, 898128000.0, -618710400.0, 239500800.0,
     -39916800.0};
-__constant__ int c_sigpoly_off[12] = {0, 2, 5, 9, 14, 20, 27, 35, 44, 54, 65, 77};
-__constant__ double c_inv_fact[12] = {1.0, 1.0, 0.5, 0.16666666666666666, 0.041666666666666664, 0.008333333333333333,
+static __constant__ int c_sigpoly_off[12] = {0, 2, 5, 9, 14, 20, 27, 35, 44, 54, 65, 77};
+static __constant__ double c_inv_fact[12] = {1.0, 1.0, 0.5, 0.16666666666666666, 0.041666666666666664, 0.008333333333333333,
                                       0.001388888888888889, 0.0001984126984126984, 2.48015873015873e-05,
                                       2.7557319223985893e-06, 2.755731922398589e-07, 2.505210838544172e-08};
 
@@ -50,6 +50,7 @@ struct RadialBuildArgs {
     double* table[2];
 };
 
+#ifdef FF_RADIAL_TABLE_KERNELS      // the two kernels are instantiated by exactly one translation unit (capi.cu)
 __global__ void __launch_bounds__(128) radial_table_build_kernel(const RadialBuildArgs a) {
     __shared__ double tab[kTabDoubles];
     __shared__ double red[128];
@@ -98,6 +99,8 @@ __global__ void __launch_bounds__(128) radial_table_build_kernel(const RadialBui
     }
 }
 
+#endif
+
 // f, f', f'', f''' of the expansion around node k at offset t
 __device__ __forceinline__ void radial_taylor(const double* __restrict__ c, double t, double (&f)[4]) {
     double p0 = c[kRtDeg], p1 = 0.0, p2 = 0.0, p3 = 0.0;
@@ -109,6 +112,7 @@ __device__ __forceinline__ void radial_taylor(const double* __restrict__ c, doub
 }
 
 // Certification: neighbouring expansions must agree at the interval mid-points.
+#ifdef FF_RADIAL_TABLE_KERNELS
 __global__ void __launch_bounds__(128) radial_table_check_kernel(double* T0, double* T1) {
     double* T = blockIdx.y ? T1 : T0;
     if (T == nullptr) return;
@@ -138,6 +142,8 @@ __global__ void __launch_bounds__(128) radial_table_check_kernel(double* T0, dou
         if (!ok) T[3] = 0.0;
     }
 }
+
+#endif
 
 // Table header in registers (loop invariant of a sweep: load it once per thread).
 struct RtHeader {
