@@ -1,7 +1,7 @@
 // C ABI, E_loc sweep (ff_eloc): statically specialised kernels for the particle numbers of the BASELINE.json configs,
 // generic flow_kernel<MODE_ELOC> otherwise.  Separate translation unit (the kernels dominate the build time).
 #include "capi_flow.h"
-#include "ff_eloc2.cuh"
+#include "ff_eloc4.cuh"
 
 using namespace ffc;
 
@@ -34,10 +34,81 @@ int launch_eloc2(ff::FlowArgs& a, cudaStream_t st) {
     return launch_flow_kernel(ff::eloc2_kernel<SN, SMU>, a, q.threads, smem, st);
 }
 
-// Statically specialised E_loc sweeps (ff_eloc2.cuh) for the particle numbers of the BASELINE.json configs; anything
+// Geometry of the finale kernel's walker block: [state: y, L, gDelta, (Delta, lapDelta), J D8 x DP][Slater scratch,
+// g0, reduction buffer][M = J J^T][x0]
+int plan_finale(ff::FlowArgs& a, int W) {
+    const int n = a.n, D = 2 * n, D8 = (D + 7) & ~7, DP = D8 + 4, NP = n * (n - 1) / 2;
+    a.D = D; a.DP = DP; a.NP = NP; a.W = W;
+    a.NSV = even(3 * D + 2 + D8 * DP);
+    a.off_sl = a.NSV;
+    const int scratch = ff::slater_scratch_size(a.n_up, n - a.n_up) + D + n * n + NP + 8 + D;
+    a.off_AM = even(a.off_sl + scratch);
+    a.off_x0 = a.off_AM + D8 * DP;
+    a.wstride = even(a.off_x0 + D);
+    return 2 * ((NP + 7) / 8) + 2 + W * a.wstride;          // doubles of dynamic shared memory
+}
+
+// Register-resident sweep (ff_eloc4.cuh eloc4_kernel) + finale kernel from the final states in global memory.
+template <int SN, int SMU>
+int launch_eloc4(ff::FlowArgs& a, cudaStream_t st) {
+    constexpr ff::Eloc4Geom g = ff::eloc4_geom(SN, SMU != 0);
+    const DevInfo di = dev_info();
+    if (a.B < 1) return 0;
+    const size_t smem = (size_t)g.total * 8;
+    if ((long long)smem > di.smem_optin) return FF_FALLBACK;
+    double* fin = nullptr;
+    FF_CUDA(cudaMallocAsync((void**)&fin, (size_t)a.B * g.fin_stride * sizeof(double), st));
+    struct Release { double* p; cudaStream_t s; ~Release() { cudaFreeAsync(p, s); } } release{fin, st};
+    auto kernel = ff::eloc4_kernel<SN, SMU>;
+    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two walkers per SM; what is left of the 256 KB stays L1 (the Taylor tables of the radial functions live there)
+    const int carve = (int)std::min<long long>(100, (2 * ((long long)smem + di.smem_reserved) * 100 + di.smem_sm - 1) / di.smem_sm);
+    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    int occ = 0;
+    FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, g.threads, smem));
+    if (occ < 1) return FF_FALLBACK;
+    const long long grid = std::min<long long>(a.B, (long long)di.sms * occ);
+#ifdef FF_ELOC4_DEBUG
+    const int dbg = getenv("FF_DBG") ? atoi(getenv("FF_DBG")) : 0;
+    FF_CUDA(cudaMemsetAsync(fin, 0, (size_t)a.B * g.fin_stride * sizeof(double), st));
+    if (dbg != 2)
+#endif
+    kernel<<<(unsigned)grid, g.threads, smem, st>>>(a, fin);
+    FF_LAUNCHED();
+#ifdef FF_ELOC4_DEBUG
+    FF_CUDA(cudaStreamSynchronize(st));
+    fprintf(stderr, "eloc4 sweep kernel finished\n");
+    if (dbg == 1) return 0;
+#endif
+    // finale: W walkers per CTA
+    ff::FlowArgs f = a;
+    int W = 2;
+    size_t fsmem = (size_t)plan_finale(f, W) * 8;
+    if ((long long)fsmem > di.smem_optin) { W = 1; fsmem = (size_t)plan_finale(f, W) * 8; }
+    if ((long long)fsmem > di.smem_optin) return fail(-2, "E_loc finale: n = %d does not fit in shared memory", a.n);
+    FF_CUDA(cudaFuncSetAttribute(ff::eloc_finale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    FF_CUDA(cudaFuncSetAttribute(ff::eloc_finale_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    int focc = 0;
+    FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&focc, ff::eloc_finale_kernel, 256, fsmem));
+    if (focc < 1) return fail(-2, "E_loc finale kernel does not fit");
+    const long long fgrid = std::min<long long>((a.B + W - 1) / W, (long long)di.sms * focc);
+    ff::eloc_finale_kernel<<<(unsigned)fgrid, 256, fsmem, st>>>(f, fin, g.fin_stride);
+    FF_LAUNCHED();
+    return 0;
+}
+
+// Statically specialised E_loc sweeps (ff_eloc4.cuh; ff_eloc2.cuh under option "eloc_v2" or without the Taylor tables) for the particle numbers of the BASELINE.json configs; anything
 // else, or "eloc_generic", runs the generic flow_kernel<MODE_ELOC>.
 int try_eloc_static(ff::FlowArgs& a, cudaStream_t st) {
     if (opt(OPT_ELOC_GENERIC) || a.H_mu <= 0) return FF_FALLBACK;
+    if (!opt(OPT_ELOC_V2) && a.rt_eta != nullptr) {
+        switch (a.n) {
+            case 20: return launch_eloc4<20, 1>(a, st);
+            case 12: return launch_eloc4<12, 1>(a, st);
+            case 6: return launch_eloc4<6, 1>(a, st);
+            default: break;
+        }
+    }
     switch (a.n) {
         case 20: return launch_eloc2<20, 1>(a, st);
         case 12: return launch_eloc2<12, 1>(a, st);

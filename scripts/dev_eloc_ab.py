@@ -1,27 +1,27 @@
-"""A/B: second-generation E_loc sweep (ff_eloc2.cuh) against the generic flow_kernel<MODE_ELOC>
-(oracle-validated) on the same walkers; prints max relative differences and timings."""
+"""E_loc sweep time (CUDA events) at N = 20: default (eloc4) against option eloc_v2, and agreement of the two."""
 import os, sys, argparse
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
+from fermiflow_b200 import _lib
 torch.set_default_dtype(torch.float64)
 dev = torch.device("cuda:0")
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 args = argparse.Namespace(hidden=50, ode_steps=16, nup=10, ndown=10, Z=2.0)
 model = bench.build_model(args, dev)
 _, x = model.sample((B,))
-def run(v1):
-    var = os.environ.get("FF_AB_VARIANT", "FF_ELOC_V3")
-    if v1: os.environ.pop(var, None); os.environ["FF_NO_STATIC"] = "1"
-    else: os.environ[var] = "1"; os.environ.pop("FF_NO_STATIC", None)
-    r = model.local_energy(x, stash=True); torch.cuda.synchronize()
+def t(stash):
+    r = model.local_energy(x, stash=stash); del r; torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); r = model.local_energy(x, stash=True); e1.record(); torch.cuda.synchronize()
-    return r, e0.elapsed_time(e1)
-ra, ta = run(True)
-rb, tb = run(False)
-print("walkers %d: generic %.2f ms, variant %.2f ms" % (B, ta, tb))
+    ts = []
+    for _ in range(3):
+        e0.record(); r = model.local_energy(x, stash=stash); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1)); del r
+    return min(ts)
+res = {}
+for v2 in (0, 1):
+    with _lib.options(eloc_v2=v2):
+        print("eloc_v2=%d: eloc %.2f ms   eloc+stash %.2f ms" % (v2, t(False), t(True)), flush=True)
+        res[v2] = model.local_energy(x[:4096], stash=True)
 for k in ("z", "logp", "grad", "lap", "kinetic", "potential", "eloc"):
-    a, b = getattr(ra, k), getattr(rb, k)
-    print("  %-10s max rel diff %.3e" % (k, float((a - b).abs().max() / a.abs().max())))
-for k, (a, b) in enumerate(((ra.stash.y, rb.stash.y), (ra.stash.c, rb.stash.c))):
-    print("  stash[%d]   max rel diff %.3e" % (k, float((a - b).abs().max() / a.abs().max())))
+    a, b = getattr(res[0], k), getattr(res[1], k)
+    print(k, float((a - b).abs().max() / b.abs().max()))
+print("stash y", float((res[0].stash.y - res[1].stash.y).abs().max()), "c", float((res[0].stash.c - res[1].stash.c).abs().max()))
