@@ -68,18 +68,8 @@ int launch_eloc4(ff::FlowArgs& a, cudaStream_t st) {
     FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, g.threads, smem));
     if (occ < 1) return FF_FALLBACK;
     const long long grid = std::min<long long>(a.B, (long long)di.sms * occ);
-#ifdef FF_ELOC4_DEBUG
-    const int dbg = getenv("FF_DBG") ? atoi(getenv("FF_DBG")) : 0;
-    FF_CUDA(cudaMemsetAsync(fin, 0, (size_t)a.B * g.fin_stride * sizeof(double), st));
-    if (dbg != 2)
-#endif
     kernel<<<(unsigned)grid, g.threads, smem, st>>>(a, fin);
     FF_LAUNCHED();
-#ifdef FF_ELOC4_DEBUG
-    FF_CUDA(cudaStreamSynchronize(st));
-    fprintf(stderr, "eloc4 sweep kernel finished\n");
-    if (dbg == 1) return 0;
-#endif
     // finale: W walkers per CTA
     ff::FlowArgs f = a;
     int W = 2;
@@ -120,6 +110,15 @@ int try_eloc_static(ff::FlowArgs& a, cudaStream_t st) {
 }  // namespace
 
 extern "C" {
+
+#ifdef FF_E4_TIMING
+int ff_debug_e4_cycles(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, ff::g_e4_cyc, sizeof(unsigned long long) * 64);
+    if (reset) { unsigned long long z[64] = {}; cudaMemcpyToSymbol(ff::g_e4_cyc, z, sizeof z); }
+    return 0;
+}
+#endif
 
 int ff_eloc(const ff_model* m, const double* x, long long B, const int* orb, const int* walker_state,
             double Z, int harmonic, double* z, double* delta_logp, double* logp, double* grad,

@@ -29,17 +29,18 @@
 
 namespace ff {
 
-#ifdef FF_ELOC4_DEBUG
-#define E4DBG(tag) do { if (blockIdx.x == 0 && lane == 0) printf("w%d st%d %s\n", warp, stage, tag); } while (0)
+#ifdef FF_E4_TIMING
+__device__ unsigned long long g_e4_cyc[4][16];
+#define E4T(seg) do { if (obs >= 0 && lane == 0) { const long long t_ = clock64(); atomicAdd(&g_e4_cyc[obs][seg], (unsigned long long)(t_ - tprev)); tprev = t_; } } while (0)
 #else
-#define E4DBG(tag) do { } while (0)
+#define E4T(seg) do { } while (0)
 #endif
 
 struct Eloc4Geom {
     int n, D, D8, DP, NP, P, NB, ntri, MAT;
     int threads, nwarp, OW, GW;
     // offsets (doubles) inside the walker block
-    int oKs, oA, oM, oG, oY, oYB, oYC, oL, oLB, oLC, oU, oKLx, oAL, oP1, oP2, oScal, total;
+    int oKs, oA, oM, oG, oKB, oKC, oY, oYB, oYC, oL, oLB, oLC, oU, oKLx, oAL, oAL2, oP1, oP2, oScal, total;
     int fin_stride;      // doubles per walker of the final state: y, L, gDelta, (Delta, lapDelta), J[D][D]
 };
 __host__ __device__ constexpr Eloc4Geom eloc4_geom(int n, bool has_mu) {
@@ -53,10 +54,12 @@ __host__ __device__ constexpr Eloc4Geom eloc4_geom(int n, bool has_mu) {
     g.oA = off; off += g.MAT;
     g.oM = off; off += g.MAT;
     g.oG = off; off = ff_even(off + g.P * kGRec);
+    // RK partials of K: [row block][owner thread] double2, conflict-free 16-byte accesses
+    g.oKB = off; off += 2 * g.NB * 32 * g.OW; g.oKC = off; off += 2 * g.NB * 32 * g.OW;
     // vectors padded to D8 (zero beyond D: the owners' K u reads whole blocks of 8)
     g.oY = off; off += g.D8; g.oYB = off; off += g.D8; g.oYC = off; off += g.D8;
     g.oL = off; off += g.D8; g.oLB = off; off += g.D8; g.oLC = off; off += g.D8;
-    g.oU = off; off += g.D8; g.oKLx = off; off += g.D8; g.oAL = off; off += g.D8;
+    g.oU = off; off += g.D8; g.oKLx = off; off += g.D8; g.oAL = off; off += g.D8; g.oAL2 = off; off += g.D8;
     g.oP1 = off; off += ff_even(n); g.oP2 = off; off += ff_even(n);
     g.oScal = off; off += 8;           // Delta, B, C, lapDelta, B, C, u.L, -
     g.total = ff_even(off);
@@ -180,79 +183,86 @@ __device__ __forceinline__ void phase_gram_t(double* M, const double* Ks, int mw
         if (on[q]) *reinterpret_cast<double2*>(Mo[q]) = make_double2(acc[q][0][0] + acc[q][1][0], acc[q][0][1] + acc[q][1][1]);
 }
 
+// Opaque copy of a lane-dependent index, taken once per RK stage: everything derived from it (dozens of shared-memory
+// addresses of the gathers, the contractions and the tensor-core fragments) is then recomputed inside the stage with
+// a handful of integer instructions instead of being hoisted out of the stage loop, where those loop invariants filled
+// the register file and spilled to local memory (first version: 120 M local loads per 9472 walkers).
+__device__ __forceinline__ int stage_local(int v) { asm volatile("" : "+r"(v)); return v; }
+
 template <int SN, int SMU>
 __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_kernel(const FlowArgs a, double* __restrict__ fin) {
     extern __shared__ __align__(16) double smem[];
     constexpr Eloc4Geom G_ = eloc4_geom(SN, SMU != 0);
     constexpr int n = G_.n, D = G_.D, DP = G_.DP, NP = G_.NP, P = G_.P, MAT = G_.MAT, NB = G_.NB;
     constexpr int NT = G_.threads, OW = G_.OW, GW = G_.GW, NOWN = 32 * OW, NGRM = 32 * GW;
-    constexpr bool has_mu = SMU != 0;
     static_assert(eloc4_supported(SN, SMU != 0), "eloc4_kernel: particle number not supported");
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g8 = lane >> 2, t4 = lane & 3;
-    const bool owner = warp < OW;
-    const int gl = tid - NOWN;                        // index inside the non-owner ("Gram") group
+    const int tid0 = threadIdx.x;
 
     double* const S = smem;
-    double* const Ks = S + G_.oKs;
-    double* const A = S + G_.oA;
-    double* const M = S + G_.oM;
-    double* const Gb = S + G_.oG;
-    double* const Y = S + G_.oY;
-    double* const L = S + G_.oL;
-    double* const U = S + G_.oU;
-    double* const scal = S + G_.oScal;
-
     // item of this lane (one item per lane: P <= NT)
-    const bool it_valid = tid < P;
-    const int it_p = it_valid ? tid : 0;
-    const bool it_pair = it_p < NP;
-    int it_i, it_j;
-    if (it_pair) {
-        int i = 0, rem = it_p;
-        while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
-        it_i = i; it_j = i + 1 + rem;
-    } else { it_i = it_p - NP; it_j = it_i; }
-    double* const Grec = Gb + it_p * kGRec;
-    const RtHeader my_rt = rt_load_header(it_pair ? a.rt_eta : a.rt_mu);
-    // gather-1 output of this owner lane: particle q >> 3, component {0, 1, 2, 3, 6, 8, 9, 10}[q & 7]
-    const int g1_i = tid >> 3, g1_k = tid & 7;
-    const int g1_c = g1_k < 4 ? g1_k : (g1_k == 4 ? 6 : g1_k + 3);
-    const bool g1_on = owner && g1_i < n;
-    // gather-2 output of this Gram-group lane: particle gl / 3, component {4, 5, 7}[gl % 3]
-    const int g2_i = gl / 3, g2_k = gl - 3 * g2_i;
-    const int g2_c = g2_k < 2 ? 4 + g2_k : 7;
-    const bool g2_on = !owner && g2_i < n;
-
+    int it_i0, it_j0;
+    {
+        const int p0 = tid0 < P ? tid0 : 0;
+        if (p0 < NP) {
+            int i = 0, rem = p0;
+            while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+            it_i0 = i; it_j0 = i + 1 + rem;
+        } else { it_i0 = p0 - NP; it_j0 = it_i0; }
+    }
     const double h = (a.tb - a.ta) / a.nsteps;
     const int NS = 4 * a.nsteps;
 
-    for (int e = tid; e < MAT; e += NT) { A[e] = 0.0; M[e] = 0.0; Ks[e] = 0.0; }      // zero padding, once
-    for (int e = G_.oY + tid; e < G_.total; e += NT) S[e] = 0.0;
+    for (int e = tid0; e < 3 * MAT; e += NT) S[e] = 0.0;                              // Ks, A, M: zero padding, once
+    for (int e = G_.oY + tid0; e < G_.total; e += NT) S[e] = 0.0;
     __syncthreads();
 
     for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
         // ---- initial state: y = x, K = 1, everything else 0 ----------------------------------------------------
-        double Kr[NB][2], KB[NB][2], KC[NB][2];
+        double Kr[NB][2];
         double gd = 0.0, gdB = 0.0, gdC = 0.0;
+        {
+            const int warp = tid0 >> 5, g8 = (tid0 >> 2) & 7, t4 = tid0 & 3;
 #pragma unroll
-        for (int rb = 0; rb < NB; ++rb)
+            for (int rb = 0; rb < NB; ++rb)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                Kr[rb][e] = (owner && 8 * warp + g8 == 8 * rb + 2 * t4 + e && 8 * warp + g8 < D) ? 1.0 : 0.0;
-                KB[rb][e] = 0.0; KC[rb][e] = 0.0;
-            }
-        for (int e = tid; e < D; e += NT) {
-            Y[e] = a.x_in[b * D + e];
-            L[e] = 0.0; S[G_.oLB + e] = 0.0; S[G_.oLC + e] = 0.0; S[G_.oYB + e] = 0.0; S[G_.oYC + e] = 0.0;
-            S[G_.oAL + e] = 0.0; S[G_.oKLx + e] = 0.0;
+                for (int e = 0; e < 2; ++e)
+                    Kr[rb][e] = (warp < OW && 8 * warp + g8 == 8 * rb + 2 * t4 + e && 8 * warp + g8 < D) ? 1.0 : 0.0;
         }
-        if (tid < 8) scal[tid] = 0.0;
+        for (int e = tid0; e < D; e += NT) {
+            S[G_.oY + e] = a.x_in[b * D + e];
+            S[G_.oL + e] = 0.0; S[G_.oLB + e] = 0.0; S[G_.oLC + e] = 0.0; S[G_.oYB + e] = 0.0; S[G_.oYC + e] = 0.0;
+            S[G_.oAL + e] = 0.0; S[G_.oAL2 + e] = 0.0; S[G_.oKLx + e] = 0.0;
+        }
+        if (tid0 < 8) S[G_.oScal + tid0] = 0.0;
         double rx = 0, ry = 0, ca = 0, cb_ = 0, ccq = 0, ceq = 0;
         __syncthreads();
+#ifdef FF_E4_TIMING
+        const int obs = (tid0 >> 5) == 0 ? 0 : (tid0 >> 5) == 1 ? 1 : (tid0 >> 5) == 5 ? 2 : (tid0 >> 5) == 7 ? 3 : -1;
+        const int lane = tid0 & 31;
+        long long tprev = clock64();
+#endif
 
         for (int stage = 0; stage <= NS; ++stage) {
             const int sub = stage & 3;
+            E4T(15);
+            // lane indices of this stage (see stage_local)
+            const int tid = stage_local(tid0);
+            const int warp = tid >> 5, g8 = (tid >> 2) & 7, t4 = tid & 3;
+            const bool owner = warp < OW;
+            const int gl = tid - NOWN;                        // index inside the non-owner ("Gram") group
+            const bool it_valid = tid < P;
+            const int it_p = it_valid ? tid : 0;
+            const bool it_pair = it_p < NP;
+            const int it_i = stage_local(it_i0), it_j = stage_local(it_j0);
+            double* const Ks = S + G_.oKs;
+            double* const A = S + G_.oA;
+            double* const M = S + G_.oM;
+            double* const Gb = S + G_.oG;
+            double* const Y = S + G_.oY;
+            double* const L = S + G_.oL;
+            double* const U = S + G_.oU;
+            double* const scal = S + G_.oScal;
+            double* const Grec = Gb + it_p * kGRec;
             // ======== phase 1 (all warps): M-contractions of the previous stage, items of this stage ============
             if (owner) {            // K of this stage for the Gram warps
 #pragma unroll
@@ -263,11 +273,18 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
                 const int i2 = 2 * it_i, j2 = 2 * it_j;
                 double w00, w01, w11;
                 if (it_pair) {
-                    w00 = M[i2 * DP + i2] + M[j2 * DP + j2] - 2.0 * M[i2 * DP + j2];
-                    w11 = M[(i2 + 1) * DP + i2 + 1] + M[(j2 + 1) * DP + j2 + 1] - 2.0 * M[(i2 + 1) * DP + j2 + 1];
-                    w01 = M[i2 * DP + i2 + 1] + M[j2 * DP + j2 + 1] - M[i2 * DP + j2 + 1] - M[(i2 + 1) * DP + j2];
+                    const double2 mii0 = *reinterpret_cast<const double2*>(M + i2 * DP + i2);
+                    const double mii1 = M[(i2 + 1) * DP + i2 + 1];
+                    const double2 mjj0 = *reinterpret_cast<const double2*>(M + j2 * DP + j2);
+                    const double mjj1 = M[(j2 + 1) * DP + j2 + 1];
+                    const double2 mij0 = *reinterpret_cast<const double2*>(M + i2 * DP + j2);
+                    const double2 mij1 = *reinterpret_cast<const double2*>(M + (i2 + 1) * DP + j2);
+                    w00 = mii0.x + mjj0.x - 2.0 * mij0.x;
+                    w11 = mii1 + mjj1 - 2.0 * mij1.y;
+                    w01 = mii0.y + mjj0.y - mij0.y - mij1.x;
                 } else {
-                    w00 = M[i2 * DP + i2]; w01 = M[i2 * DP + i2 + 1]; w11 = M[(i2 + 1) * DP + i2 + 1];
+                    const double2 mii0 = *reinterpret_cast<const double2*>(M + i2 * DP + i2);
+                    w00 = mii0.x; w01 = mii0.y; w11 = M[(i2 + 1) * DP + i2 + 1];
                 }
                 const double wrx = fma(w00, rx, w01 * ry), wry = fma(w01, rx, w11 * ry);
                 const double trw = w00 + w11, rwr = fma(rx, wrx, ry * wry);
@@ -278,13 +295,19 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
             if (stage < NS) {
                 if (a.stash_y != nullptr && tid < D) a.stash_y[(b * NS + stage) * D + tid] = Y[tid];
                 if (it_valid) {
-                    if (it_pair) { rx = Y[2 * it_i] - Y[2 * it_j]; ry = Y[2 * it_i + 1] - Y[2 * it_j + 1]; }
-                    else { rx = Y[2 * it_i]; ry = Y[2 * it_i + 1]; }
+                    if (it_pair) {
+                        const double2 yi = *reinterpret_cast<const double2*>(Y + 2 * it_i), yj = *reinterpret_cast<const double2*>(Y + 2 * it_j);
+                        rx = yi.x - yj.x; ry = yi.y - yj.y;
+                    } else {
+                        const double2 yi = *reinterpret_cast<const double2*>(Y + 2 * it_i);
+                        rx = yi.x; ry = yi.y;
+                    }
+                    const RtHeader my_rt = rt_load_header(it_pair ? a.rt_eta : a.rt_mu);
                     const double d2 = fma(rx, rx, ry * ry);
                     const double inv_d = rsqrt(d2);
                     const double d = d2 * inv_d;
                     double f[4];
-                    if (!radial_table_eval_l1(my_rt, d, f))
+                    if (!radial_table_eval<3>(my_rt, d, f))
                         radial_direct_global(it_pair ? a.eta_w1 : a.mu_w1, it_pair ? a.eta_b1 : a.mu_b1,
                                              it_pair ? a.eta_w2 : a.mu_w2, it_pair ? a.H_eta : a.H_mu, d, f);
                     if (a.stash_c != nullptr) {
@@ -314,13 +337,17 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
                     }
                 }
             }
-            E4DBG("p1 done");
+            E4T(0);
             __syncthreads();
+            E4T(1);
             // ======== phase 2 ===================================================================================
             if (owner) {
                 if (stage < NS) {
                     // ---- per-particle sums of this stage: k_y (y advances here), u, rho, diagonal of A ----------
-                    if (g1_on) {
+                    // output of this lane: particle tid >> 3, component {0, 1, 2, 3, 6, 8, 9, 10}[tid & 7]
+                    const int g1_i = tid >> 3, g1_k = tid & 7;
+                    const int g1_c = g1_k < 4 ? g1_k : (g1_k == 4 ? 6 : g1_k + 3);
+                    if (g1_i < n) {
                         const double acc = gather_sum<SN, SMU>(Gb, g1_i, g1_c);
                         if (g1_c < 2) {
                             const int m = 2 * g1_i + g1_c;
@@ -331,10 +358,10 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
                         else if (g1_c == 9) { A[a_row(2 * g1_i) * DP + 2 * g1_i + 1] = acc; A[a_row(2 * g1_i + 1) * DP + 2 * g1_i] = acc; }
                         else A[a_row(2 * g1_i + 1) * DP + 2 * g1_i + 1] = acc;
                     }
-                    E4DBG("own gather done");
+                    E4T(2);
                     named_bar_sync(1, NOWN);              // A, u complete (owner warps)
-                    named_bar_arrive(2, NT);
-                    E4DBG("own bar1 passed");              // ... and visible to the Gram group when it gets there
+                    named_bar_arrive(2, NT);              // ... and visible to the Gram group when it gets there
+                    E4T(3);
                     // ---- K' = K A on the tensor cores, k-step (rb, e): A operand = own registers ---------------
                     double acc[NB][2];
 #pragma unroll
@@ -356,6 +383,7 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
 #pragma unroll
                         for (int rn = 0; rn < NB; ++rn) bc[rn] = bn[rn];
                     }
+                    E4T(4);
                     // ---- K u (for gDelta' = -u^T J): row sums over the quad ------------------------------------
                     double ku = 0.0;
 #pragma unroll
@@ -366,32 +394,44 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
                     }
                     ku += __shfl_xor_sync(0xffffffffu, ku, 1);
                     ku += __shfl_xor_sync(0xffffffffu, ku, 2);
-                    // ---- RK update in registers ------------------------------------------------------------------
+                    // ---- RK update: K in registers, its two partials in shared memory ---------------------------
+                    double2* const PB = reinterpret_cast<double2*>(S + G_.oKB) + tid;
+                    double2* const PC = reinterpret_cast<double2*>(S + G_.oKC) + tid;
 #pragma unroll
                     for (int rn = 0; rn < NB; ++rn) {
-                        Kr[rn][0] = rk_elem(sub, Kr[rn][0], h * acc[rn][0], KB[rn][0], KC[rn][0]);
-                        Kr[rn][1] = rk_elem(sub, Kr[rn][1], h * acc[rn][1], KB[rn][1], KC[rn][1]);
+                        double2 Bv = make_double2(0.0, 0.0), Cv = make_double2(0.0, 0.0);
+                        if (sub == 1 || sub == 2) Bv = PB[rn * NOWN];
+                        if (sub >= 1) Cv = PC[rn * NOWN];
+                        Kr[rn][0] = rk_elem(sub, Kr[rn][0], h * acc[rn][0], Bv.x, Cv.x);
+                        Kr[rn][1] = rk_elem(sub, Kr[rn][1], h * acc[rn][1], Bv.y, Cv.y);
+                        if (sub <= 1) PB[rn * NOWN] = Bv;
+                        if (sub <= 2) PC[rn * NOWN] = Cv;
                     }
                     gd = rk_elem(sub, gd, -h * ku, gdB, gdC);
-                    E4DBG("own done");
+                    E4T(5);
                 }
             } else {
                 // ---- M = K^T K of this stage (consumed by the contractions at the start of the next stage) ------
-                if (stage < NS) phase_gram_t<SN, SMU, GW>(M, Ks, warp - OW, lane);
-                E4DBG("gram done");
+                if (stage < NS) phase_gram_t<SN, SMU, GW>(M, Ks, warp - OW, tid & 31);
+                E4T(2);
                 // ---- previous stage: per-particle sums of the M-contractions, then L and lapDelta advance ------
                 if (stage > 0) {
                     const int psub = (stage - 1) & 3;
-                    if (g2_on) {
+                    // output of this lane: particle gl / 3, component {4, 5, 7}[gl % 3]
+                    const int g2_i = gl / 3, g2_k = gl - 3 * g2_i;
+                    const int g2_c = g2_k < 2 ? 4 + g2_k : 7;
+                    if (g2_i < n) {
                         const double acc = gather_sum<SN, SMU>(Gb, g2_i, g2_c);
                         if (g2_c < 6) S[G_.oKLx + 2 * g2_i + g2_c - 4] = acc; else S[G_.oP2 + g2_i] = acc;
                     }
+                    E4T(3);
                     named_bar_sync(3, NGRM);
                     if (gl < D) {
-                        const double kL = S[G_.oAL + gl] + S[G_.oKLx + gl];
+                        const double kL = (S[G_.oAL + gl] + S[G_.oAL2 + gl]) + S[G_.oKLx + gl];
                         L[gl] = rk_elem(psub, L[gl], h * kL, S[G_.oLB + gl], S[G_.oLC + gl]);
                     }
                     if (warp == OW) {           // lapDelta' = -(sum_i part2_i + u.L)
+                        const int lane = tid & 31;
                         double lp = lane < n ? S[G_.oP2 + lane] : 0.0;
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
@@ -400,26 +440,26 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
                     named_bar_sync(3, NGRM);
                 }
                 if (stage < NS) {
-                    E4DBG("gram at bar2");
+                    E4T(4);
                     named_bar_sync(2, NT);              // the owners' sums of this stage are in place: A, u, rho
-                    E4DBG("gram bar2 passed");
+                    E4T(5);
                     // ---- A L and u.L of this stage (with the L just completed), Delta advances ----------------
-                    {
-                        const int m = gl >> 1, half = gl & 1;
-                        constexpr int HD = D / 2;
-                        double s = 0.0;
-                        if (gl < 2 * D) {
-                            const double* Ar = A + a_row(m) * DP + half * HD;
-                            const double* Lh = L + half * HD;
-                            double s0 = 0.0, s1 = 0.0;
+                    // lane (m, half): sum over the rows k = 2 q + half of A[k][m] L[k] (A symmetric: column m read along
+                    // the lanes, conflict free; the rows of parity `half` sit 4 physical rows apart)
+                    if (gl < 2 * D) {
+                        const int half = gl >= D ? 1 : 0, m = gl - half * D;
+                        const double* Ac = A + half * 4 * DP + m;
+                        const double* Lh = L + half;
+                        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                            for (int k = 0; k < HD; ++k) { if (k & 1) s1 = fma(Ar[k], Lh[k], s1); else s0 = fma(Ar[k], Lh[k], s0); }
-                            s = s0 + s1;
+                        for (int q = 0; q < D / 2; ++q) {
+                            const double av = Ac[a_row(2 * q) * DP], lv = Lh[2 * q];
+                            if (q & 1) s1 = fma(av, lv, s1); else s0 = fma(av, lv, s0);
                         }
-                        s += __shfl_xor_sync(0xffffffffu, s, 1);          // whole warp: the last one is only partly busy
-                        if (gl < 2 * D && half == 0) S[G_.oAL + m] = s;
+                        S[(half ? G_.oAL2 : G_.oAL) + m] = s0 + s1;
                     }
                     if (warp == NT / 32 - 1) {
+                        const int lane = tid & 31;
                         double ul = 0.0, rho = 0.0;
                         for (int k = lane; k < D; k += 32) ul = fma(U[k], L[k], ul);
                         if (lane < n) rho = S[G_.oP1 + lane];
@@ -435,15 +475,18 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
                     }
                 }
             }
+            E4T(6);
             __syncthreads();
+            E4T(7);
         }
         // ---- final state to global memory: y, L, gDelta, (Delta, lapDelta), J = K^T row-major --------------------
         double* F = fin + (size_t)b * G_.fin_stride;
-        for (int e = tid; e < D; e += NT) { F[e] = Y[e]; F[D + e] = L[e]; }
-        if (tid == 0) { F[3 * D] = scal[0]; F[3 * D + 1] = scal[3]; }
-        if (owner) {
+        for (int e = tid0; e < D; e += NT) { F[e] = S[G_.oY + e]; F[D + e] = S[G_.oL + e]; }
+        if (tid0 == 0) { F[3 * D] = S[G_.oScal]; F[3 * D + 1] = S[G_.oScal + 3]; }
+        {
+            const int warp = tid0 >> 5, g8 = (tid0 >> 2) & 7, t4 = tid0 & 3;
             const int c = 8 * warp + g8;
-            if (c < D) {
+            if (warp < OW && c < D) {
                 if (t4 == 0) F[2 * D + c] = gd;
 #pragma unroll
                 for (int rb = 0; rb < NB; ++rb)
@@ -454,8 +497,8 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
                     }
             }
         }
-        if (a.y_out) for (int e = tid; e < D; e += NT) a.y_out[b * D + e] = Y[e];
-        if (a.delta_out && tid == 0) a.delta_out[b] = scal[0];
+        if (a.y_out) for (int e = tid0; e < D; e += NT) a.y_out[b * D + e] = S[G_.oY + e];
+        if (a.delta_out && tid0 == 0) a.delta_out[b] = S[G_.oScal];
         __syncthreads();
     }
 }
