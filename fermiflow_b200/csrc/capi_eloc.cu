@@ -1,7 +1,7 @@
 // C ABI, E_loc sweep (ff_eloc): statically specialised kernels for the particle numbers of the BASELINE.json configs,
 // generic flow_kernel<MODE_ELOC> otherwise.  Separate translation unit (the kernels dominate the build time).
 #include "capi_flow.h"
-#include "ff_eloc4.cuh"
+#include "ff_eloc5.cuh"
 
 using namespace ffc;
 
@@ -48,29 +48,9 @@ int plan_finale(ff::FlowArgs& a, int W) {
     return 2 * ((NP + 7) / 8) + 2 + W * a.wstride;          // doubles of dynamic shared memory
 }
 
-// Register-resident sweep (ff_eloc4.cuh eloc4_kernel) + finale kernel from the final states in global memory.
-template <int SN, int SMU>
-int launch_eloc4(ff::FlowArgs& a, cudaStream_t st) {
-    constexpr ff::Eloc4Geom g = ff::eloc4_geom(SN, SMU != 0);
+// Finale kernel from the final states in global memory (fin: `stride` doubles per walker).
+int launch_finale(const ff::FlowArgs& a, const double* fin, int stride, cudaStream_t st) {
     const DevInfo di = dev_info();
-    if (a.B < 1) return 0;
-    const size_t smem = (size_t)g.total * 8;
-    if ((long long)smem > di.smem_optin) return FF_FALLBACK;
-    double* fin = nullptr;
-    FF_CUDA(cudaMallocAsync((void**)&fin, (size_t)a.B * g.fin_stride * sizeof(double), st));
-    struct Release { double* p; cudaStream_t s; ~Release() { cudaFreeAsync(p, s); } } release{fin, st};
-    auto kernel = ff::eloc4_kernel<SN, SMU>;
-    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // two walkers per SM; what is left of the 256 KB stays L1 (the Taylor tables of the radial functions live there)
-    const int carve = (int)std::min<long long>(100, (2 * ((long long)smem + di.smem_reserved) * 100 + di.smem_sm - 1) / di.smem_sm);
-    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    int occ = 0;
-    FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, g.threads, smem));
-    if (occ < 1) return FF_FALLBACK;
-    const long long grid = std::min<long long>(a.B, (long long)di.sms * occ);
-    kernel<<<(unsigned)grid, g.threads, smem, st>>>(a, fin);
-    FF_LAUNCHED();
-    // finale: W walkers per CTA
     ff::FlowArgs f = a;
     int W = 2;
     size_t fsmem = (size_t)plan_finale(f, W) * 8;
@@ -82,9 +62,42 @@ int launch_eloc4(ff::FlowArgs& a, cudaStream_t st) {
     FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&focc, ff::eloc_finale_kernel, 256, fsmem));
     if (focc < 1) return fail(-2, "E_loc finale kernel does not fit");
     const long long fgrid = std::min<long long>((a.B + W - 1) / W, (long long)di.sms * focc);
-    ff::eloc_finale_kernel<<<(unsigned)fgrid, 256, fsmem, st>>>(f, fin, g.fin_stride);
+    ff::eloc_finale_kernel<<<(unsigned)fgrid, 256, fsmem, st>>>(f, fin, stride);
     FF_LAUNCHED();
     return 0;
+}
+
+// Register-resident sweeps (ff_eloc5.cuh eloc5_kernel: specialised owner / worker warps; ff_eloc4.cuh eloc4_kernel under
+// option "eloc_v4") + finale kernel.
+template <class Kernel>
+int launch_eloc_reg(Kernel kernel, int threads, size_t smem, int fin_stride, ff::FlowArgs& a, cudaStream_t st) {
+    const DevInfo di = dev_info();
+    if (a.B < 1) return 0;
+    if ((long long)smem > di.smem_optin) return FF_FALLBACK;
+    double* fin = nullptr;
+    FF_CUDA(cudaMallocAsync((void**)&fin, (size_t)a.B * fin_stride * sizeof(double), st));
+    struct Release { double* p; cudaStream_t s; ~Release() { cudaFreeAsync(p, s); } } release{fin, st};
+    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two walkers per SM; what is left of the 256 KB stays L1 (the Taylor tables of the radial functions live there)
+    const int carve = (int)std::min<long long>(100, (2 * ((long long)smem + di.smem_reserved) * 100 + di.smem_sm - 1) / di.smem_sm);
+    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    int occ = 0;
+    FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+    if (occ < 1) return FF_FALLBACK;
+    const long long grid = std::min<long long>(a.B, (long long)di.sms * occ);
+    kernel<<<(unsigned)grid, threads, smem, st>>>(a, fin);
+    FF_LAUNCHED();
+    return launch_finale(a, fin, fin_stride, st);
+}
+template <int SN, int SMU>
+int launch_eloc4(ff::FlowArgs& a, cudaStream_t st) {
+    constexpr ff::Eloc4Geom g = ff::eloc4_geom(SN, SMU != 0);
+    return launch_eloc_reg(ff::eloc4_kernel<SN, SMU>, g.threads, (size_t)g.total * 8, g.fin_stride, a, st);
+}
+template <int SN, int SMU>
+int launch_eloc5(ff::FlowArgs& a, cudaStream_t st) {
+    constexpr ff::Eloc5Geom g = ff::eloc5_geom(SN, SMU != 0);
+    return launch_eloc_reg(ff::eloc5_kernel<SN, SMU>, g.threads, (size_t)g.total * 8, g.fin_stride, a, st);
 }
 
 // Statically specialised E_loc sweeps (ff_eloc4.cuh; ff_eloc2.cuh under option "eloc_v2" or without the Taylor tables) for the particle numbers of the BASELINE.json configs; anything
@@ -92,10 +105,18 @@ int launch_eloc4(ff::FlowArgs& a, cudaStream_t st) {
 int try_eloc_static(ff::FlowArgs& a, cudaStream_t st) {
     if (opt(OPT_ELOC_GENERIC) || a.H_mu <= 0) return FF_FALLBACK;
     if (!opt(OPT_ELOC_V2) && a.rt_eta != nullptr) {
+        if (opt(OPT_ELOC_V4)) {
+            switch (a.n) {
+                case 20: return launch_eloc4<20, 1>(a, st);
+                case 12: return launch_eloc4<12, 1>(a, st);
+                case 6: return launch_eloc4<6, 1>(a, st);
+                default: break;
+            }
+        }
         switch (a.n) {
-            case 20: return launch_eloc4<20, 1>(a, st);
-            case 12: return launch_eloc4<12, 1>(a, st);
-            case 6: return launch_eloc4<6, 1>(a, st);
+            case 20: return launch_eloc5<20, 1>(a, st);
+            case 12: return launch_eloc5<12, 1>(a, st);
+            case 6: return launch_eloc5<6, 1>(a, st);
             default: break;
         }
     }
@@ -116,6 +137,14 @@ int ff_debug_e4_cycles(unsigned long long* out, int reset) {
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out, ff::g_e4_cyc, sizeof(unsigned long long) * 64);
     if (reset) { unsigned long long z[64] = {}; cudaMemcpyToSymbol(ff::g_e4_cyc, z, sizeof z); }
+    return 0;
+}
+#endif
+#ifdef FF_E5_TIMING
+int ff_debug_e5_cycles(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, ff::g_e5_cyc, sizeof(unsigned long long) * 64);
+    if (reset) { unsigned long long z[64] = {}; cudaMemcpyToSymbol(ff::g_e5_cyc, z, sizeof z); }
     return 0;
 }
 #endif

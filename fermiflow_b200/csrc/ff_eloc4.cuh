@@ -40,7 +40,7 @@ struct Eloc4Geom {
     int n, D, D8, DP, NP, P, NB, ntri, MAT;
     int threads, nwarp, OW, GW;
     // offsets (doubles) inside the walker block
-    int oKs, oA, oM, oG, oKB, oKC, oY, oYB, oYC, oL, oLB, oLC, oU, oKLx, oAL, oAL2, oP1, oP2, oScal, total;
+    int RP, RMAT, oKs, oA, oM, oR1, oG2, oKB, oKC, oY, oYB, oYC, oL, oLB, oLC, oU, oKLx, oAL, oAL2, oP1, oP2, oScal, total;
     int fin_stride;      // doubles per walker of the final state: y, L, gDelta, (Delta, lapDelta), J[D][D]
 };
 __host__ __device__ constexpr Eloc4Geom eloc4_geom(int n, bool has_mu) {
@@ -53,7 +53,12 @@ __host__ __device__ constexpr Eloc4Geom eloc4_geom(int n, bool has_mu) {
     g.oKs = off; off += g.MAT;
     g.oA = off; off += g.MAT;
     g.oM = off; off += g.MAT;
-    g.oG = off; off = ff_even(off + g.P * kGRec);
+    // per-particle sums of the stage: five n x n matrices R_c[i][k] (k_y x/y, u x/y, rho; both orientations of every
+    // pair, the one-body item on the diagonal; odd row pitch) -- the gather is a plain row sum --, three-component
+    // records of the M-contractions per item
+    g.RP = n | 1; g.RMAT = n * g.RP;
+    g.oR1 = off; off = ff_even(off + 5 * g.RMAT);
+    g.oG2 = off; off = ff_even(off + 3 * g.P);
     // RK partials of K: [row block][owner thread] double2, conflict-free 16-byte accesses
     g.oKB = off; off += 2 * g.NB * 32 * g.OW; g.oKC = off; off += 2 * g.NB * 32 * g.OW;
     // vectors padded to D8 (zero beyond D: the owners' K u reads whole blocks of 8)
@@ -117,28 +122,24 @@ __device__ __forceinline__ bool radial_table_eval_l1(const RtHeader& T, double d
     return true;
 }
 
-// Per-particle sums of NC record components (list CL) for output q = (particle i = q / NC, component CL[q % NC]).
-// Partner slot k < i is pair (k, i) at record K_k + i (K_k a compile-time constant), slot k >= i is pair (i, k + 1) at
-// record U_i + k + 1: one select + one load + one FMA per term.  Components < 6 change sign with the orientation of
-// the pair, 6 and 7 are counted once per pair (their records hold the pair total: halved here), the mu item of the
-// particle is added last.
+// Per-particle sum of component c < 3 of the three-component records G2[p][3] of the M-contractions.  Partner slot
+// k < i is pair (k, i) at record K_k + i (K_k a compile-time constant), slot k >= i is pair (i, k + 1) at record
+// U_i + k + 1.  Components 0, 1 change sign with the orientation of the pair, component 2 holds the pair total (halved
+// here); the one-body item of the particle is added last.
 template <int SN, int SMU>
-__device__ __forceinline__ double gather_sum(const double* __restrict__ Gb, int i, int c) {
+__device__ __forceinline__ double gather3(const double* __restrict__ G2, int i, int c) {
     constexpr int n = SN, NP = SN * (SN - 1) / 2;
-    const double* pL = Gb + i * kGRec + c;                                             // + 11 * (K_k - k - 1)
-    const double* pU = Gb + (i * (2 * n - i - 1) / 2 - i - 1) * kGRec + c;             // + 11 * (k + 1)
-    const double slo = (c < 6) ? -1.0 : 1.0;
-    double acc0 = 0.0, acc1 = 0.0;
+    const double* pL = G2 + 3 * i + c;                                             // + 3 * (K_k - k - 1)
+    const double* pU = G2 + 3 * (i * (2 * n - i - 1) / 2 - i - 1) + c;             // + 3 * (k + 1)
+    double lo0 = 0.0, lo1 = 0.0, up0 = 0.0, up1 = 0.0;
 #pragma unroll
     for (int k = 0; k < n - 1; ++k) {
-        const bool lower = k < i;
-        const double* ad = lower ? pL + (k * (2 * n - k - 1) / 2 - k - 1) * kGRec : pU + (k + 1) * kGRec;
-        const double v = *ad, sg = lower ? slo : 1.0;
-        if (k & 1) acc1 = fma(v, sg, acc1); else acc0 = fma(v, sg, acc0);
+        if (k < i) { const double v = pL[3 * (k * (2 * n - k - 1) / 2 - k - 1)]; if (k & 1) lo1 += v; else lo0 += v; }
+        else { const double v = pU[3 * (k + 1)]; if (k & 1) up1 += v; else up0 += v; }
     }
-    double acc = acc0 + acc1;
-    if (c == 6 || c == 7) acc *= 0.5;
-    if (SMU != 0) acc += Gb[(NP + i) * kGRec + c];
+    const double lo = lo0 + lo1, up = up0 + up1;
+    double acc = c < 2 ? up - lo : 0.5 * (up + lo);
+    if (SMU != 0) acc += G2[3 * (NP + i) + c];
     return acc;
 }
 
@@ -212,8 +213,7 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
     const double h = (a.tb - a.ta) / a.nsteps;
     const int NS = 4 * a.nsteps;
 
-    for (int e = tid0; e < 3 * MAT; e += NT) S[e] = 0.0;                              // Ks, A, M: zero padding, once
-    for (int e = G_.oY + tid0; e < G_.total; e += NT) S[e] = 0.0;
+    for (int e = tid0; e < G_.total; e += NT) S[e] = 0.0;                             // zero padding of the matrices and vectors, once
     __syncthreads();
 
     for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
@@ -257,12 +257,12 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
             double* const Ks = S + G_.oKs;
             double* const A = S + G_.oA;
             double* const M = S + G_.oM;
-            double* const Gb = S + G_.oG;
+            double* const R1 = S + G_.oR1;
+            double* const G2 = S + G_.oG2 + 3 * it_p;
             double* const Y = S + G_.oY;
             double* const L = S + G_.oL;
             double* const U = S + G_.oU;
             double* const scal = S + G_.oScal;
-            double* const Grec = Gb + it_p * kGRec;
             // ======== phase 1 (all warps): M-contractions of the previous stage, items of this stage ============
             if (owner) {            // K of this stage for the Gram warps
 #pragma unroll
@@ -288,9 +288,9 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
                 }
                 const double wrx = fma(w00, rx, w01 * ry), wry = fma(w01, rx, w11 * ry);
                 const double trw = w00 + w11, rwr = fma(rx, wrx, ry * wry);
-                Grec[4] = fma(ca, fma(2.0, wrx, trw * rx), cb_ * rwr * rx);
-                Grec[5] = fma(ca, fma(2.0, wry, trw * ry), cb_ * rwr * ry);
-                Grec[7] = fma(ccq, trw, ceq * rwr);
+                G2[0] = fma(ca, fma(2.0, wrx, trw * rx), cb_ * rwr * rx);
+                G2[1] = fma(ca, fma(2.0, wry, trw * ry), cb_ * rwr * ry);
+                G2[2] = fma(ccq, trw, ceq * rwr);
             }
             if (stage < NS) {
                 if (a.stash_y != nullptr && tid < D) a.stash_y[(b * NS + stage) * D + tid] = Y[tid];
@@ -324,16 +324,27 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
                     ccq = q1 * inv_d;
                     ceq = (q2 - ccq) * inv_d2;
                     const double a00 = fma(ca * rx, rx, cf), a01 = ca * rx * ry, a11 = fma(ca * ry, ry, cf);
-                    Grec[0] = cf * rx; Grec[1] = cf * ry;
-                    Grec[2] = ccq * rx; Grec[3] = ccq * ry;
-                    Grec[6] = mult * fma(f[1], d, 2.0 * f[0]);
-                    Grec[8] = a00; Grec[9] = a01; Grec[10] = a11;
-                    if (it_pair) {          // off-diagonal blocks of A = dv/dy (row-permuted storage)
+                    const double v0 = cf * rx, v1 = cf * ry, v2 = ccq * rx, v3 = ccq * ry, v4 = fma(f[1], d, 2.0 * f[0]);
+                    constexpr int RP = G_.RP, RMAT = G_.RMAT;
+                    if (it_pair) {          // both orientations of the pair; off-diagonal blocks of A = dv/dy (row-permuted storage)
+                        double* const Rij = R1 + it_i * RP + it_j;
+                        double* const Rji = R1 + it_j * RP + it_i;
+                        Rij[0] = v0; Rji[0] = -v0;
+                        Rij[RMAT] = v1; Rji[RMAT] = -v1;
+                        Rij[2 * RMAT] = v2; Rji[2 * RMAT] = -v2;
+                        Rij[3 * RMAT] = v3; Rji[3 * RMAT] = -v3;
+                        Rij[4 * RMAT] = v4; Rji[4 * RMAT] = v4;
                         const int i2 = 2 * it_i, j2 = 2 * it_j;
                         *reinterpret_cast<double2*>(A + a_row(i2) * DP + j2) = make_double2(-a00, -a01);
                         *reinterpret_cast<double2*>(A + a_row(i2 + 1) * DP + j2) = make_double2(-a01, -a11);
                         *reinterpret_cast<double2*>(A + a_row(j2) * DP + i2) = make_double2(-a00, -a01);
                         *reinterpret_cast<double2*>(A + a_row(j2 + 1) * DP + i2) = make_double2(-a01, -a11);
+                    } else {                // one-body item: diagonal of the matrices, minus its block in the diagonal slot of A
+                        double* const Rii = R1 + it_i * (RP + 1);
+                        Rii[0] = v0; Rii[RMAT] = v1; Rii[2 * RMAT] = v2; Rii[3 * RMAT] = v3; Rii[4 * RMAT] = v4;
+                        const int i2 = 2 * it_i;
+                        *reinterpret_cast<double2*>(A + a_row(i2) * DP + i2) = make_double2(-a00, -a01);
+                        A[a_row(i2 + 1) * DP + i2 + 1] = -a11;
                     }
                 }
             }
@@ -344,18 +355,35 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
             if (owner) {
                 if (stage < NS) {
                     // ---- per-particle sums of this stage: k_y (y advances here), u, rho, diagonal of A ----------
-                    // output of this lane: particle tid >> 3, component {0, 1, 2, 3, 6, 8, 9, 10}[tid & 7]
-                    const int g1_i = tid >> 3, g1_k = tid & 7;
-                    const int g1_c = g1_k < 4 ? g1_k : (g1_k == 4 ? 6 : g1_k + 3);
-                    if (g1_i < n) {
-                        const double acc = gather_sum<SN, SMU>(Gb, g1_i, g1_c);
-                        if (g1_c < 2) {
-                            const int m = 2 * g1_i + g1_c;
+                    // output of this lane: row sum c8 = tid / n of particle i = tid % n: matrices 0..4 (k_y, u, rho) or,
+                    // c8 = 5, 6, 7, the diagonal block (0,0), (0,1), (1,1) of A = minus the sum of the off-diagonal
+                    // blocks of its rows (the slot of the diagonal block itself holds minus the one-body part)
+                    const int c8 = tid / n, g1_i = tid - c8 * n;
+                    if (c8 < 8) {
+                        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                        if (c8 < 5) {
+                            const double* R = R1 + c8 * G_.RMAT + g1_i * G_.RP;
+#pragma unroll
+                            for (int k = 0; k < n; ++k) {
+                                const double v = R[k];
+                                if ((k & 3) == 0) s0 += v; else if ((k & 3) == 1) s1 += v; else if ((k & 3) == 2) s2 += v; else s3 += v;
+                            }
+                        } else {
+                            const double* Ar = A + a_row(2 * g1_i + (c8 == 7 ? 1 : 0)) * DP + (c8 >= 6 ? 1 : 0);
+#pragma unroll
+                            for (int k = 0; k < n; ++k) {
+                                const double v = (SMU != 0 || k != g1_i) ? Ar[2 * k] : 0.0;
+                                if ((k & 3) == 0) s0 -= v; else if ((k & 3) == 1) s1 -= v; else if ((k & 3) == 2) s2 -= v; else s3 -= v;
+                            }
+                        }
+                        const double acc = (s0 + s1) + (s2 + s3);
+                        if (c8 < 2) {
+                            const int m = 2 * g1_i + c8;
                             Y[m] = rk_elem(sub, Y[m], h * acc, S[G_.oYB + m], S[G_.oYC + m]);
-                        } else if (g1_c < 4) U[2 * g1_i + g1_c - 2] = acc;
-                        else if (g1_c == 6) S[G_.oP1 + g1_i] = acc;
-                        else if (g1_c == 8) A[a_row(2 * g1_i) * DP + 2 * g1_i] = acc;
-                        else if (g1_c == 9) { A[a_row(2 * g1_i) * DP + 2 * g1_i + 1] = acc; A[a_row(2 * g1_i + 1) * DP + 2 * g1_i] = acc; }
+                        } else if (c8 < 4) U[2 * g1_i + c8 - 2] = acc;
+                        else if (c8 == 4) S[G_.oP1 + g1_i] = acc;
+                        else if (c8 == 5) A[a_row(2 * g1_i) * DP + 2 * g1_i] = acc;
+                        else if (c8 == 6) { A[a_row(2 * g1_i) * DP + 2 * g1_i + 1] = acc; A[a_row(2 * g1_i + 1) * DP + 2 * g1_i] = acc; }
                         else A[a_row(2 * g1_i + 1) * DP + 2 * g1_i + 1] = acc;
                     }
                     E4T(2);
@@ -417,12 +445,11 @@ __global__ void __launch_bounds__(eloc4_geom(SN, SMU != 0).threads, 2) eloc4_ker
                 // ---- previous stage: per-particle sums of the M-contractions, then L and lapDelta advance ------
                 if (stage > 0) {
                     const int psub = (stage - 1) & 3;
-                    // output of this lane: particle gl / 3, component {4, 5, 7}[gl % 3]
+                    // output of this lane: particle gl / 3, component gl % 3 of the contraction records
                     const int g2_i = gl / 3, g2_k = gl - 3 * g2_i;
-                    const int g2_c = g2_k < 2 ? 4 + g2_k : 7;
                     if (g2_i < n) {
-                        const double acc = gather_sum<SN, SMU>(Gb, g2_i, g2_c);
-                        if (g2_c < 6) S[G_.oKLx + 2 * g2_i + g2_c - 4] = acc; else S[G_.oP2 + g2_i] = acc;
+                        const double acc = gather3<SN, SMU>(S + G_.oG2, g2_i, g2_k);
+                        if (g2_k < 2) S[G_.oKLx + 2 * g2_i + g2_k] = acc; else S[G_.oP2 + g2_i] = acc;
                     }
                     E4T(3);
                     named_bar_sync(3, NGRM);

@@ -1,0 +1,488 @@
+// E_loc sweep, register-resident Jacobian with specialised warps (eloc5_kernel); finale in eloc_finale_kernel.
+//
+// Same mathematics as flow_body<MODE_ELOC> (ff_flow.cuh; replaces utils.py:44-65 y_grad_laplacian + VMC.py:41-55 on
+// top of flow.py:42-56 / equivariant_funs.py:17-102): the forward-mode state (y, J, L, gDelta, Delta, lapDelta) of ONE
+// walker per CTA is integrated with the 3/8-rule RK4 (torchdiffeq rk4_alt_step_func).  As in eloc4_kernel the Jacobian
+// is carried transposed, K = J^T, in the accumulator layout of mma.m8n8k4 in the registers of NB "owner" warps (those
+// registers are the A operand of K' = K A, see ff_eloc4.cuh), its RK partials in shared memory.  What is different:
+//
+//   * The CTA has NB owner warps and WW = ceil(P / 32) "worker" warps (N = 20: 5 + 7 = 384 threads at 80 registers,
+//     two CTAs = 24 warps per SM instead of 16).  Owners never evaluate items, workers never hold K: neither side
+//     carries the other's registers.
+//   * Two CTA barriers per RK stage, and both kinds of warps have work in both phases:
+//       phase 1   workers: finish the items of the stage from (r and the radial functions) kept in registers -- matrices R_c of the
+//                 per-particle sums, off-diagonal blocks of A = dv/dy, stash.
+//                 owners: M = K^T K on the tensor cores from the shared copy of K (owners 1..3 at NB = 5, so that every
+//                 scheduler sees 100 DMMA per stage: owners 0 and 4 share one and have the larger part of K A).
+//       phase 2   owners: row sums (k_y: y advances; u, rho, diagonal of A), K A on the tensor cores, K u, RK update of
+//                 K in registers, shared copy of the new K.
+//                 workers: contractions of their items with M, per-particle sums of those, A L, RK update of L, Delta,
+//                 lapDelta -- and then the radial functions (certified Taylor tables) of the NEXT stage at the y the
+//                 owners have just advanced: the long-latency table look-up overlaps the owners' tensor-core work.
+//   * Nothing lags: M of stage s is formed in phase 1 of stage s and consumed in its phase 2.
+#pragma once
+#include "ff_eloc4.cuh"
+
+namespace ff {
+
+struct Eloc5Geom {
+    int n, D, D8, DP, NP, P, NB, ntri, MAT, RP, RMAT;
+    int threads, OW, WW, G0, GWN;
+    int oKs, oA, oM, oR1, oG2, oKB, oKC, oY, oYB, oYC, oL0, oL1, oLB, oLC, oU, oKLx, oP1, oP2, oScal, total;
+    int fin_stride;
+};
+__host__ __device__ constexpr Eloc5Geom eloc5_geom(int n, bool has_mu) {
+    Eloc5Geom g{};
+    g.n = n; g.D = 2 * n; g.D8 = (g.D + 7) & ~7; g.DP = g.D8 + 4;
+    g.NP = n * (n - 1) / 2; g.P = g.NP + (has_mu ? n : 0);
+    g.NB = g.D8 / 8; g.ntri = g.NB * (g.NB + 1) / 2; g.MAT = g.D8 * g.DP;
+    g.OW = g.NB; g.WW = (g.P + 31) / 32; g.threads = 32 * (g.OW + g.WW);
+    // owner warps that form the Gram matrix in phase 1
+    g.G0 = g.NB >= 5 ? 1 : 0; g.GWN = g.NB >= 5 ? 3 : g.NB;
+    g.RP = n | 1; g.RMAT = n * g.RP;
+    int off = 0;
+    g.oKs = off; off += g.MAT;
+    g.oA = off; off += g.MAT;
+    g.oM = off; off += g.MAT;
+    g.oR1 = off; off = ff_even(off + 5 * g.RMAT);
+    g.oG2 = off; off = ff_even(off + 3 * g.P);
+    g.oKB = off; off += 2 * g.NB * 32 * g.OW; g.oKC = off; off += 2 * g.NB * 32 * g.OW;
+    g.oY = off; off += g.D8; g.oYB = off; off += g.D8; g.oYC = off; off += g.D8;
+    g.oL0 = off; off += g.D8; g.oL1 = off; off += g.D8; g.oLB = off; off += g.D8; g.oLC = off; off += g.D8;
+    g.oU = off; off += g.D8; g.oKLx = off; off += g.D8;
+    g.oP1 = off; off += ff_even(n); g.oP2 = off; off += ff_even(n);
+    g.oScal = off; off += 8;           // Delta, B, C, lapDelta, B, C
+    g.total = ff_even(off);
+    g.fin_stride = 3 * g.D + 2 + g.D * g.D;
+    return g;
+}
+__host__ __device__ constexpr bool eloc5_supported(int n, bool has_mu) {
+    const Eloc5Geom g = eloc5_geom(n, has_mu);
+    return g.NB >= 1 && g.NB <= 5 && 8 * n <= 32 * g.OW && 3 * n <= 32 * g.WW && g.D <= 32 * g.WW && n <= 32 &&
+           (g.ntri + g.GWN - 1) / g.GWN <= 5 && g.threads <= 384;
+}
+
+// M = K^T K (upper block triangle, logical row-major) from K row-major in shared memory.  `code` packs (row block,
+// column block) of the NBW blocks of this warp, 6 bits each (a loop invariant of the sweep: one register).
+template <int SN, int SMU>
+__device__ __forceinline__ int gram5_code(int mwarp) {
+    constexpr Eloc5Geom G_ = eloc5_geom(SN, SMU != 0);
+    constexpr int NB = G_.NB, MW = G_.GWN, NBW = (G_.ntri + MW - 1) / MW;
+    int code = 0;
+    for (int q = 0; q < NBW; ++q) {
+        const int blk = mwarp + q * MW;
+        int rb = 0, rem = blk < G_.ntri ? blk : 0;
+        while (rem >= NB - rb) { rem -= NB - rb; ++rb; }
+        code |= (rb | ((rb + rem) << 3)) << (6 * q);
+    }
+    return code;
+}
+template <int SN, int SMU>
+__device__ __forceinline__ void phase_gram5(double* M, const double* Ks, int mwarp, int code, int lane) {
+    constexpr Eloc5Geom G_ = eloc5_geom(SN, SMU != 0);
+    constexpr int D8 = G_.D8, DP = G_.DP, KS = D8 / 4, MW = G_.GWN, NBW = (G_.ntri + MW - 1) / MW;
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const double* Ar[NBW]; const double* Br[NBW];
+#pragma unroll
+    for (int q = 0; q < NBW; ++q) {
+        const int rb = (code >> (6 * q)) & 7, cb = (code >> (6 * q + 3)) & 7;
+        Ar[q] = Ks + t4 * DP + 8 * rb + g8;
+        Br[q] = Ks + t4 * DP + 8 * cb + g8;
+    }
+    double acc[NBW][2][2];
+#pragma unroll
+    for (int q = 0; q < NBW; ++q) { acc[q][0][0] = acc[q][0][1] = acc[q][1][0] = acc[q][1][1] = 0.0; }
+    double fa[NBW], fb[NBW], na[NBW], nb[NBW];
+#pragma unroll
+    for (int q = 0; q < NBW; ++q) { fa[q] = lds_ordered(Ar[q]); fb[q] = lds_ordered(Br[q]); na[q] = nb[q] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        if (k + 1 < KS) {
+#pragma unroll
+            for (int q = 0; q < NBW; ++q) { na[q] = lds_ordered(Ar[q] + 4 * (k + 1) * DP); nb[q] = lds_ordered(Br[q] + 4 * (k + 1) * DP); }
+        }
+#pragma unroll
+        for (int q = 0; q < NBW; ++q) dmma_ordered(acc[q][k & 1][0], acc[q][k & 1][1], fa[q], fb[q]);
+#pragma unroll
+        for (int q = 0; q < NBW; ++q) { fa[q] = na[q]; fb[q] = nb[q]; }
+    }
+#pragma unroll
+    for (int q = 0; q < NBW; ++q) {
+        const int rb = (code >> (6 * q)) & 7, cb = (code >> (6 * q + 3)) & 7;
+        if (mwarp + q * MW < G_.ntri)
+            *reinterpret_cast<double2*>(M + (8 * rb + g8) * DP + 8 * cb + 2 * t4) =
+                make_double2(acc[q][0][0] + acc[q][1][0], acc[q][0][1] + acc[q][1][1]);
+    }
+}
+
+#ifdef FF_E5_TIMING
+__device__ unsigned long long g_e5_cyc[4][16];
+#define E5T(seg) do { if (obs >= 0 && (tid0 & 31) == 0) { const long long t_ = clock64(); atomicAdd(&g_e5_cyc[obs][seg], (unsigned long long)(t_ - tprev)); tprev = t_; } } while (0)
+#else
+#define E5T(seg) do { } while (0)
+#endif
+
+template <int SN, int SMU>
+__global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_kernel(const FlowArgs a, double* __restrict__ fin) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr Eloc5Geom G_ = eloc5_geom(SN, SMU != 0);
+    constexpr int n = G_.n, D = G_.D, DP = G_.DP, NP = G_.NP, P = G_.P, NB = G_.NB;
+    constexpr int NT = G_.threads, OW = G_.OW, WW = G_.WW, NOWN = 32 * OW, NWRK = 32 * WW;
+    constexpr int RP = G_.RP, RMAT = G_.RMAT;
+    static_assert(eloc5_supported(SN, SMU != 0), "eloc5_kernel: particle number not supported");
+    const int tid0 = threadIdx.x;
+    const bool owner0 = tid0 < NOWN;
+
+    double* const S = smem;
+    const double h = (a.tb - a.ta) / a.nsteps;
+    const int NS = 4 * a.nsteps;
+
+    for (int e = tid0; e < G_.total; e += NT) S[e] = 0.0;                             // zero padding of the matrices and vectors, once
+    __syncthreads();
+
+    // Owners and workers run their own stage loops (the register allocation is the larger of the two, not their sum);
+    // the CTA barriers inside are barrier 0 with all NT threads on both sides.
+    if (owner0) {
+        const int gcode = gram5_code<SN, SMU>(max((tid0 >> 5) - G_.G0, 0));
+        for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+            // ---- initial state: K = 1 (registers and shared copy), gDelta = 0; y = x -------------------------------
+            double Kr[NB][2];
+            double gd = 0.0, gdB = 0.0, gdC = 0.0;
+            {
+                const int warp = tid0 >> 5, g8 = (tid0 >> 2) & 7, t4 = tid0 & 3;
+#pragma unroll
+                for (int rb = 0; rb < NB; ++rb) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        Kr[rb][e] = (8 * warp + g8 == 8 * rb + 2 * t4 + e && 8 * warp + g8 < D) ? 1.0 : 0.0;
+                    *reinterpret_cast<double2*>(S + G_.oKs + (8 * warp + g8) * DP + 8 * rb + 2 * t4) = make_double2(Kr[rb][0], Kr[rb][1]);
+                }
+            }
+            for (int e = tid0; e < D; e += NOWN) {
+                S[G_.oY + e] = a.x_in[b * D + e];
+                S[G_.oL0 + e] = 0.0; S[G_.oL1 + e] = 0.0; S[G_.oLB + e] = 0.0; S[G_.oLC + e] = 0.0; S[G_.oYB + e] = 0.0; S[G_.oYC + e] = 0.0;
+            }
+            if (tid0 < 8) S[G_.oScal + tid0] = 0.0;
+            named_bar_sync(0, NT);
+            named_bar_sync(0, NT);                       // (the workers evaluate the radial functions of stage 0)
+#ifdef FF_E5_TIMING
+            const int obs = (tid0 >> 5) == 0 ? 0 : (tid0 >> 5) == 1 ? 1 : -1;
+            long long tprev = clock64();
+#endif
+            for (int stage = 0; stage < NS; ++stage) {
+                const int sub = stage & 3;
+                E5T(15);
+                const int tid = stage_local(tid0);          // lane indices of this stage (see stage_local)
+                const int warp = tid >> 5, g8 = (tid >> 2) & 7, t4 = tid & 3;
+                double* const Ks = S + G_.oKs;
+                double* const A = S + G_.oA;
+                double* const R1 = S + G_.oR1;
+                double* const Y = S + G_.oY;
+                double* const U = S + G_.oU;
+                // ======== phase 1: M = K^T K of this stage ==========================================================
+                if (warp >= G_.G0 && warp < G_.G0 + G_.GWN) phase_gram5<SN, SMU>(S + G_.oM, Ks, warp - G_.G0, stage_local(gcode), tid & 31);
+                E5T(0);
+                named_bar_sync(0, NT);
+                E5T(1);
+                // ======== phase 2 ===================================================================================
+                // ---- per-particle sums of this stage: k_y (y advances here), u, rho, diagonal of A -----------------
+                // output of this lane: row sum c8 = tid / n of particle i = tid % n: matrices 0..4 (k_y, u, rho) or,
+                // c8 = 5, 6, 7, the diagonal block (0,0), (0,1), (1,1) of A = minus the sum of the off-diagonal blocks
+                // of its rows (the slot of the diagonal block itself holds minus the one-body part)
+                {
+                    const int c8 = tid / n, g1_i = tid - c8 * n;
+                    if (c8 < 8) {
+                        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                        if (c8 < 5) {
+                            const double* R = R1 + c8 * RMAT + g1_i * RP;
+#pragma unroll
+                            for (int k = 0; k < n; ++k) {
+                                const double v = R[k];
+                                if ((k & 3) == 0) s0 += v; else if ((k & 3) == 1) s1 += v; else if ((k & 3) == 2) s2 += v; else s3 += v;
+                            }
+                        } else {
+                            const double* Ar = A + a_row(2 * g1_i + (c8 == 7 ? 1 : 0)) * DP + (c8 >= 6 ? 1 : 0);
+#pragma unroll
+                            for (int k = 0; k < n; ++k) {
+                                const double v = (SMU != 0 || k != g1_i) ? Ar[2 * k] : 0.0;
+                                if ((k & 3) == 0) s0 -= v; else if ((k & 3) == 1) s1 -= v; else if ((k & 3) == 2) s2 -= v; else s3 -= v;
+                            }
+                        }
+                        const double acc = (s0 + s1) + (s2 + s3);
+                        if (c8 < 2) {
+                            const int m = 2 * g1_i + c8;
+                            Y[m] = rk_elem(sub, Y[m], h * acc, S[G_.oYB + m], S[G_.oYC + m]);
+                        } else if (c8 < 4) U[2 * g1_i + c8 - 2] = acc;
+                        else if (c8 == 4) S[G_.oP1 + g1_i] = acc;
+                        else if (c8 == 5) A[a_row(2 * g1_i) * DP + 2 * g1_i] = acc;
+                        else if (c8 == 6) { A[a_row(2 * g1_i) * DP + 2 * g1_i + 1] = acc; A[a_row(2 * g1_i + 1) * DP + 2 * g1_i] = acc; }
+                        else A[a_row(2 * g1_i + 1) * DP + 2 * g1_i + 1] = acc;
+                    }
+                }
+                E5T(2);
+                named_bar_sync(1, NOWN);              // A, u, y complete (owner warps)
+                named_bar_arrive(2, NT);              // ... and visible to the workers when they get there
+                E5T(3);
+                // ---- K' = K A on the tensor cores, k-step (rb, e): A operand = own registers -----------------------
+                double acc[NB][2];
+#pragma unroll
+                for (int rn = 0; rn < NB; ++rn) { acc[rn][0] = 0.0; acc[rn][1] = 0.0; }
+                {
+                    const double* Ab = A + t4 * DP + g8;
+                    double bn[NB], bc[NB];
+#pragma unroll
+                    for (int rn = 0; rn < NB; ++rn) bc[rn] = lds_ordered(Ab + 8 * rn);
+#pragma unroll
+                    for (int ks = 0; ks < 2 * NB; ++ks) {
+                        const int rb = ks >> 1, e = ks & 1;
+                        if (ks + 1 < 2 * NB) {
+                            const int rb1 = (ks + 1) >> 1, e1 = (ks + 1) & 1;
+#pragma unroll
+                            for (int rn = 0; rn < NB; ++rn) bn[rn] = lds_ordered(Ab + (8 * rb1 + 4 * e1) * DP + 8 * rn);
+                        }
+#pragma unroll
+                        for (int rn = 0; rn < NB; ++rn) dmma_ordered(acc[rn][0], acc[rn][1], Kr[rb][e], bc[rn]);
+#pragma unroll
+                        for (int rn = 0; rn < NB; ++rn) bc[rn] = bn[rn];
+                    }
+                }
+                E5T(4);
+                // ---- K u (for gDelta' = -u^T J): row sums over the quad --------------------------------------------
+                double ku = 0.0;
+#pragma unroll
+                for (int rb = 0; rb < NB; ++rb) {
+                    const double2 uv = *reinterpret_cast<const double2*>(U + 8 * rb + 2 * t4);
+                    ku = fma(Kr[rb][0], uv.x, ku);
+                    ku = fma(Kr[rb][1], uv.y, ku);
+                }
+                ku += __shfl_xor_sync(0xffffffffu, ku, 1);
+                ku += __shfl_xor_sync(0xffffffffu, ku, 2);
+                // ---- RK update: K in registers, its two partials in shared memory; shared copy of the new K --------
+                double2* const PB = reinterpret_cast<double2*>(S + G_.oKB) + tid;
+                double2* const PC = reinterpret_cast<double2*>(S + G_.oKC) + tid;
+#pragma unroll
+                for (int rn = 0; rn < NB; ++rn) {
+                    double2 Bv = make_double2(0.0, 0.0), Cv = make_double2(0.0, 0.0);
+                    if (sub == 1 || sub == 2) Bv = PB[rn * NOWN];
+                    if (sub >= 1) Cv = PC[rn * NOWN];
+                    Kr[rn][0] = rk_elem(sub, Kr[rn][0], h * acc[rn][0], Bv.x, Cv.x);
+                    Kr[rn][1] = rk_elem(sub, Kr[rn][1], h * acc[rn][1], Bv.y, Cv.y);
+                    if (sub <= 1) PB[rn * NOWN] = Bv;
+                    if (sub <= 2) PC[rn * NOWN] = Cv;
+                    *reinterpret_cast<double2*>(Ks + (8 * warp + g8) * DP + 8 * rn + 2 * t4) = make_double2(Kr[rn][0], Kr[rn][1]);
+                }
+                gd = rk_elem(sub, gd, -h * ku, gdB, gdC);
+                E5T(5);
+                named_bar_sync(0, NT);
+                E5T(7);
+            }
+            // ---- final state to global memory: gDelta, J = K^T row-major (the workers write the vectors) -----------
+            {
+                double* F = fin + (size_t)b * G_.fin_stride;
+                const int warp = tid0 >> 5, g8 = (tid0 >> 2) & 7, t4 = tid0 & 3;
+                const int c = 8 * warp + g8;
+                if (c < D) {
+                    if (t4 == 0) F[2 * D + c] = gd;
+#pragma unroll
+                    for (int rb = 0; rb < NB; ++rb)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int r = 8 * rb + 2 * t4 + e;
+                            if (r < D) F[3 * D + 2 + r * D + c] = Kr[rb][e];
+                        }
+                }
+            }
+            named_bar_sync(0, NT);
+        }
+    } else {
+        // item of this worker lane (one item per lane: P <= NWRK)
+        int it_i0 = 0, it_j0 = 0;
+        {
+            const int p0 = tid0 - NOWN < P ? tid0 - NOWN : 0;
+            if (p0 < NP) {
+                int i = 0, rem = p0;
+                while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+                it_i0 = i; it_j0 = i + 1 + rem;
+            } else { it_i0 = p0 - NP; it_j0 = it_i0; }
+        }
+        for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+            // the item of the coming stage: r, d, 1/d and the radial function with three derivatives
+            double rx = 0.0, ry = 0.0, dd = 1.0, inv_d = 1.0, f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
+            named_bar_sync(0, NT);                       // (the owners have set the initial state)
+#ifdef FF_E5_TIMING
+            const int obs = (tid0 >> 5) == OW ? 2 : (tid0 >> 5) == OW + WW - 1 ? 3 : -1;
+            long long tprev = clock64();
+#endif
+            for (int stage = -1; stage < NS; ++stage) {
+                const int sub = stage & 3;
+                E5T(15);
+                const int tid = stage_local(tid0);          // lane indices of this stage (see stage_local)
+                const int warp = tid >> 5;
+                const int wl = tid - NOWN;                  // index inside the worker group
+                const bool it_valid = wl < P;
+                const int it_p = it_valid ? wl : 0;
+                const bool it_pair = it_p < NP;
+                const int it_i = stage_local(it_i0), it_j = stage_local(it_j0);
+                double* const A = S + G_.oA;
+                double* const M = S + G_.oM;
+                double* const R1 = S + G_.oR1;
+                double* const Y = S + G_.oY;
+                double* const U = S + G_.oU;
+                double* const scal = S + G_.oScal;
+                double* const Lc = S + ((stage & 1) ? G_.oL1 : G_.oL0);          // L at the stage input
+                double* const Ln = S + ((stage & 1) ? G_.oL0 : G_.oL1);
+                if (stage >= 0) {
+                    // ======== phase 1: the items of this stage from r and the radial functions ======================
+                    double ca = 0.0, cb_ = 0.0, ccq = 0.0, ceq = 0.0;
+                    if (a.stash_y != nullptr && wl < D) a.stash_y[(b * NS + stage) * D + wl] = Y[wl];
+                    if (it_valid) {
+                        if (a.stash_c != nullptr) {
+                            double* sc = a.stash_c + ((b * NS + stage) * P + it_p) * 3;
+                            sc[0] = f0; sc[1] = f1; sc[2] = f2;
+                        }
+                        const double mult = it_pair ? 2.0 : 1.0;
+                        const double inv_d2 = inv_d * inv_d;
+                        ca = f1 * inv_d;
+                        cb_ = (f2 - ca) * inv_d2;
+                        const double q1 = mult * fma(f2, dd, 3.0 * f1);
+                        const double q2 = mult * fma(f3, dd, 4.0 * f2);
+                        ccq = q1 * inv_d;
+                        ceq = (q2 - ccq) * inv_d2;
+                        const double a00 = fma(ca * rx, rx, f0), a01 = ca * rx * ry, a11 = fma(ca * ry, ry, f0);
+                        const double v0 = f0 * rx, v1 = f0 * ry, v2 = ccq * rx, v3 = ccq * ry, v4 = fma(f1, dd, 2.0 * f0);
+                        if (it_pair) {          // both orientations of the pair; off-diagonal blocks of A (row-permuted storage)
+                            double* const Rij = R1 + it_i * RP + it_j;
+                            double* const Rji = R1 + it_j * RP + it_i;
+                            Rij[0] = v0; Rji[0] = -v0;
+                            Rij[RMAT] = v1; Rji[RMAT] = -v1;
+                            Rij[2 * RMAT] = v2; Rji[2 * RMAT] = -v2;
+                            Rij[3 * RMAT] = v3; Rji[3 * RMAT] = -v3;
+                            Rij[4 * RMAT] = v4; Rji[4 * RMAT] = v4;
+                            const int i2 = 2 * it_i, j2 = 2 * it_j;
+                            *reinterpret_cast<double2*>(A + a_row(i2) * DP + j2) = make_double2(-a00, -a01);
+                            *reinterpret_cast<double2*>(A + a_row(i2 + 1) * DP + j2) = make_double2(-a01, -a11);
+                            *reinterpret_cast<double2*>(A + a_row(j2) * DP + i2) = make_double2(-a00, -a01);
+                            *reinterpret_cast<double2*>(A + a_row(j2 + 1) * DP + i2) = make_double2(-a01, -a11);
+                        } else {                // one-body item: diagonal of the matrices, minus its block in the diagonal slot of A
+                            double* const Rii = R1 + it_i * (RP + 1);
+                            Rii[0] = v0; Rii[RMAT] = v1; Rii[2 * RMAT] = v2; Rii[3 * RMAT] = v3; Rii[4 * RMAT] = v4;
+                            const int i2 = 2 * it_i;
+                            *reinterpret_cast<double2*>(A + a_row(i2) * DP + i2) = make_double2(-a00, -a01);
+                            A[a_row(i2 + 1) * DP + i2 + 1] = -a11;
+                        }
+                    }
+                    E5T(0);
+                    named_bar_sync(0, NT);
+                    E5T(1);
+                    // ======== phase 2 ===============================================================================
+                    // ---- contraction of this lane's item with M = J J^T --------------------------------------------
+                    if (it_valid) {
+                        const int i2 = 2 * it_i, j2 = 2 * it_j;
+                        double w00, w01, w11;
+                        if (it_pair) {
+                            const double2 mii0 = *reinterpret_cast<const double2*>(M + i2 * DP + i2);
+                            const double mii1 = M[(i2 + 1) * DP + i2 + 1];
+                            const double2 mjj0 = *reinterpret_cast<const double2*>(M + j2 * DP + j2);
+                            const double mjj1 = M[(j2 + 1) * DP + j2 + 1];
+                            const double2 mij0 = *reinterpret_cast<const double2*>(M + i2 * DP + j2);
+                            const double2 mij1 = *reinterpret_cast<const double2*>(M + (i2 + 1) * DP + j2);
+                            w00 = mii0.x + mjj0.x - 2.0 * mij0.x;
+                            w11 = mii1 + mjj1 - 2.0 * mij1.y;
+                            w01 = mii0.y + mjj0.y - mij0.y - mij1.x;
+                        } else {
+                            const double2 mii0 = *reinterpret_cast<const double2*>(M + i2 * DP + i2);
+                            w00 = mii0.x; w01 = mii0.y; w11 = M[(i2 + 1) * DP + i2 + 1];
+                        }
+                        const double wrx = fma(w00, rx, w01 * ry), wry = fma(w01, rx, w11 * ry);
+                        const double trw = w00 + w11, rwr = fma(rx, wrx, ry * wry);
+                        double* const G2 = S + G_.oG2 + 3 * it_p;
+                        G2[0] = fma(ca, fma(2.0, wrx, trw * rx), cb_ * rwr * rx);
+                        G2[1] = fma(ca, fma(2.0, wry, trw * ry), cb_ * rwr * ry);
+                        G2[2] = fma(ccq, trw, ceq * rwr);
+                    }
+                    E5T(2);
+                    named_bar_sync(3, NWRK);
+                    // ---- per-particle sums of the contractions: lane (particle wl / 3, component wl % 3) -----------
+                    {
+                        const int g2_i = wl / 3, g2_k = wl - 3 * g2_i;
+                        if (g2_i < n) {
+                            const double acc = gather3<SN, SMU>(S + G_.oG2, g2_i, g2_k);
+                            if (g2_k < 2) S[G_.oKLx + 2 * g2_i + g2_k] = acc; else S[G_.oP2 + g2_i] = acc;
+                        }
+                    }
+                    E5T(3);
+                    named_bar_sync(2, NT);                // the owners' sums of this stage are in place: y, A, u, rho
+                    E5T(4);
+                    // ---- L' = A L + (d2v : M), lane m < D: column m of the symmetric A along the lanes -------------
+                    if (wl < D) {
+                        const double* Ac = A + wl;
+                        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            const double av = Ac[a_row(k) * DP], lv = Lc[k];
+                            if ((k & 3) == 0) s0 = fma(av, lv, s0); else if ((k & 3) == 1) s1 = fma(av, lv, s1);
+                            else if ((k & 3) == 2) s2 = fma(av, lv, s2); else s3 = fma(av, lv, s3);
+                        }
+                        const double kL = ((s0 + s1) + (s2 + s3)) + S[G_.oKLx + wl];
+                        Ln[wl] = rk_elem(sub, Lc[wl], h * kL, S[G_.oLB + wl], S[G_.oLC + wl]);
+                    }
+                    if (warp == OW + WW - 1) {          // Delta' = -rho, lapDelta' = -(sum_i part2_i + u.L)
+                        const int lane = tid & 31;
+                        double ul = 0.0, rho = 0.0, lp = 0.0;
+                        for (int k = lane; k < D; k += 32) ul = fma(U[k], Lc[k], ul);
+                        if (lane < n) { rho = S[G_.oP1 + lane]; lp = S[G_.oP2 + lane]; }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            ul += __shfl_xor_sync(0xffffffffu, ul, o);
+                            rho += __shfl_xor_sync(0xffffffffu, rho, o);
+                            lp += __shfl_xor_sync(0xffffffffu, lp, o);
+                        }
+                        if (lane == 0) {
+                            scal[0] = rk_elem(sub, scal[0], -h * rho, scal[1], scal[2]);
+                            scal[3] = rk_elem(sub, scal[3], -h * (lp + ul), scal[4], scal[5]);
+                        }
+                    }
+                    E5T(5);
+                }
+                // ---- radial functions of the next stage at the y just advanced (none after the last stage) ---------
+                if (stage + 1 < NS && it_valid) {
+                    if (it_pair) {
+                        const double2 yi = *reinterpret_cast<const double2*>(Y + 2 * it_i), yj = *reinterpret_cast<const double2*>(Y + 2 * it_j);
+                        rx = yi.x - yj.x; ry = yi.y - yj.y;
+                    } else {
+                        const double2 yi = *reinterpret_cast<const double2*>(Y + 2 * it_i);
+                        rx = yi.x; ry = yi.y;
+                    }
+                    const RtHeader my_rt = rt_load_header(it_pair ? a.rt_eta : a.rt_mu);
+                    const double d2 = fma(rx, rx, ry * ry);
+                    inv_d = rsqrt(d2);
+                    dd = d2 * inv_d;
+                    double f[4];
+                    if (!radial_table_eval<3>(my_rt, dd, f))
+                        radial_direct_global(it_pair ? a.eta_w1 : a.mu_w1, it_pair ? a.eta_b1 : a.mu_b1,
+                                             it_pair ? a.eta_w2 : a.mu_w2, it_pair ? a.H_eta : a.H_mu, dd, f);
+                    f0 = f[0]; f1 = f[1]; f2 = f[2]; f3 = f[3];
+                }
+                E5T(6);
+                named_bar_sync(0, NT);
+                E5T(7);
+            }
+            // ---- final state to global memory: y, L, (Delta, lapDelta) ----------------------------------------------
+            {
+                double* F = fin + (size_t)b * G_.fin_stride;
+                const int wl = tid0 - NOWN;
+                for (int e = wl; e < D; e += NWRK) {
+                    F[e] = S[G_.oY + e]; F[D + e] = S[G_.oL0 + e];       // NS is even: L ends in buffer 0
+                    if (a.y_out) a.y_out[b * D + e] = S[G_.oY + e];
+                }
+                if (wl == 0) {
+                    F[3 * D] = S[G_.oScal]; F[3 * D + 1] = S[G_.oScal + 3];
+                    if (a.delta_out) a.delta_out[b] = S[G_.oScal];
+                }
+            }
+            named_bar_sync(0, NT);
+        }
+    }
+}
+
+}  // namespace ff

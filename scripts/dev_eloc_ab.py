@@ -17,11 +17,13 @@ def t(stash):
         e0.record(); r = model.local_energy(x, stash=stash); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1)); del r
     return min(ts)
 res = {}
-for v2 in (0, 1):
-    with _lib.options(eloc_v2=v2):
-        print("eloc_v2=%d: eloc %.2f ms   eloc+stash %.2f ms" % (v2, t(False), t(True)), flush=True)
-        res[v2] = model.local_energy(x[:4096], stash=True)
+variants = [("eloc5", {}), ("eloc4", dict(eloc_v4=1)), ("eloc2", dict(eloc_v2=1))]
+for rep in range(2):
+    for v2, (name, kw) in enumerate(variants):
+        with _lib.options(**kw):
+            print("%s: eloc %.2f ms   eloc+stash %.2f ms   eloc %.2f ms" % (name, t(False), t(True), t(False)), flush=True)
+            res[v2] = model.local_energy(x[:4096], stash=True)
 for k in ("z", "logp", "grad", "lap", "kinetic", "potential", "eloc"):
-    a, b = getattr(res[0], k), getattr(res[1], k)
+    a, b = getattr(res[0], k), getattr(res[2], k)
     print(k, float((a - b).abs().max() / b.abs().max()))
-print("stash y", float((res[0].stash.y - res[1].stash.y).abs().max()), "c", float((res[0].stash.c - res[1].stash.c).abs().max()))
+print("stash y", float((res[0].stash.y - res[2].stash.y).abs().max()), "c", float((res[0].stash.c - res[2].stash.c).abs().max()))
