@@ -97,7 +97,13 @@ int launch_eloc4(ff::FlowArgs& a, cudaStream_t st) {
 template <int SN, int SMU>
 int launch_eloc5(ff::FlowArgs& a, cudaStream_t st) {
     constexpr ff::Eloc5Geom g = ff::eloc5_geom(SN, SMU != 0);
-    return launch_eloc_reg(ff::eloc5_kernel<SN, SMU>, g.threads, (size_t)g.total * 8, g.fin_stride, a, st);
+    // two CTAs per SM with the whole shared-memory carve-out: what the walker block leaves of a CTA's half mirrors the
+    // head of the eta table (ff::kRtPitch doubles per node)
+    const DevInfo di = dev_info();
+    const long long half = std::min<long long>(di.smem_sm / 2 - di.smem_reserved, di.smem_optin);
+    const long long room = half - (long long)g.total * 8;
+    a.rt_cache_nodes = (a.rt_eta != nullptr && room > 0 && !opt(OPT_NO_RT_CACHE)) ? (int)std::min<long long>(room / (8 * ff::kRtPitch), 1024) : 0;
+    return launch_eloc_reg(ff::eloc5_kernel<SN, SMU>, g.threads, (size_t)(g.total + a.rt_cache_nodes * ff::kRtPitch) * 8, g.fin_stride, a, st);
 }
 
 // Statically specialised E_loc sweeps (ff_eloc4.cuh; ff_eloc2.cuh under option "eloc_v2" or without the Taylor tables) for the particle numbers of the BASELINE.json configs; anything

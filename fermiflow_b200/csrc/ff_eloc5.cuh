@@ -28,7 +28,7 @@ namespace ff {
 struct Eloc5Geom {
     int n, D, D8, DP, NP, P, NB, ntri, MAT, RP, RMAT;
     int threads, OW, WW, G0, GWN;
-    int oKs, oA, oM, oR1, oG2, oKB, oKC, oY, oYB, oYC, oL0, oL1, oLB, oLC, oU, oKLx, oP1, oP2, oScal, total;
+    int oKs, oA, oM, oR1, oG2, oKB, oKC, oY, oYB, oYC, oL0, oL1, oLB, oLC, oU, oKLx, oP1, oP2, oScal, total;   // the mirror of the eta table starts at `total`
     int fin_stride;
 };
 __host__ __device__ constexpr Eloc5Geom eloc5_geom(int n, bool has_mu) {
@@ -62,57 +62,94 @@ __host__ __device__ constexpr bool eloc5_supported(int n, bool has_mu) {
            (g.ntri + g.GWN - 1) / g.GWN <= 5 && g.threads <= 384;
 }
 
-// M = K^T K (upper block triangle, logical row-major) from K row-major in shared memory.  `code` packs (row block,
-// column block) of the NBW blocks of this warp, 6 bits each (a loop invariant of the sweep: one register).
-template <int SN, int SMU>
-__device__ __forceinline__ int gram5_code(int mwarp) {
-    constexpr Eloc5Geom G_ = eloc5_geom(SN, SMU != 0);
-    constexpr int NB = G_.NB, MW = G_.GWN, NBW = (G_.ntri + MW - 1) / MW;
-    int code = 0;
-    for (int q = 0; q < NBW; ++q) {
-        const int blk = mwarp + q * MW;
-        int rb = 0, rem = blk < G_.ntri ? blk : 0;
-        while (rem >= NB - rb) { rem -= NB - rb; ++rb; }
-        code |= (rb | ((rb + rem) << 3)) << (6 * q);
+// Blocks of the upper block triangle of M = K^T K that Gram warp W of MW forms.  NB = 5, MW = 3: block rows {0}, {1, 4},
+// {2, 3} -- five blocks each, and the warps need only 5 / 4 / 3 distinct operand fragments per k-step.
+struct GramList { int nb; int rb[5]; int cb[5]; unsigned mask; };
+__host__ __device__ constexpr GramList gram_list(int NB, int MW, int W) {
+    GramList L{};
+    if (NB == 5 && MW == 3) {
+        const int rows[3][2] = {{0, -1}, {1, 4}, {2, 3}};
+        for (int t = 0; t < 2; ++t) {
+            const int r = rows[W][t];
+            if (r < 0) continue;
+            for (int c = r; c < NB; ++c) { L.rb[L.nb] = r; L.cb[L.nb] = c; ++L.nb; }
+        }
+    } else {
+        int blk = 0;
+        for (int r = 0; r < NB; ++r)
+            for (int c = r; c < NB; ++c, ++blk)
+                if (blk % MW == W && L.nb < 5) { L.rb[L.nb] = r; L.cb[L.nb] = c; ++L.nb; }
     }
-    return code;
+    for (int q = 0; q < L.nb; ++q) L.mask |= (1u << L.rb[q]) | (1u << L.cb[q]);
+    return L;
 }
-template <int SN, int SMU>
-__device__ __forceinline__ void phase_gram5(double* M, const double* Ks, int mwarp, int code, int lane) {
+// M = K^T K from the shared copy of K (row-major): the A and the B operand of block (rb, cb) at k-step k are the SAME kind
+// of fragment, Ks[4 k + t][8 c + g] with c = rb or cb, so a warp fetches each column-block fragment it needs once per k-step
+// (shared-memory bandwidth, not the tensor pipe, bounds this kernel).
+template <int SN, int SMU, int W>
+__device__ __forceinline__ void phase_gram5w(double* M, const double* Ks, int lane) {
     constexpr Eloc5Geom G_ = eloc5_geom(SN, SMU != 0);
-    constexpr int D8 = G_.D8, DP = G_.DP, KS = D8 / 4, MW = G_.GWN, NBW = (G_.ntri + MW - 1) / MW;
+    constexpr int D8 = G_.D8, DP = G_.DP, NB = G_.NB, KS = D8 / 4;
+    constexpr GramList GL = gram_list(G_.NB, G_.GWN, W);
     const int g8 = lane >> 2, t4 = lane & 3;
-    const double* Ar[NBW]; const double* Br[NBW];
+    const double* base = Ks + t4 * DP + g8;
+    double acc[GL.nb > 0 ? GL.nb : 1][2];
 #pragma unroll
-    for (int q = 0; q < NBW; ++q) {
-        const int rb = (code >> (6 * q)) & 7, cb = (code >> (6 * q + 3)) & 7;
-        Ar[q] = Ks + t4 * DP + 8 * rb + g8;
-        Br[q] = Ks + t4 * DP + 8 * cb + g8;
-    }
-    double acc[NBW][2][2];
+    for (int q = 0; q < GL.nb; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+    double fc[NB], fn[NB];
 #pragma unroll
-    for (int q = 0; q < NBW; ++q) { acc[q][0][0] = acc[q][0][1] = acc[q][1][0] = acc[q][1][1] = 0.0; }
-    double fa[NBW], fb[NBW], na[NBW], nb[NBW];
-#pragma unroll
-    for (int q = 0; q < NBW; ++q) { fa[q] = lds_ordered(Ar[q]); fb[q] = lds_ordered(Br[q]); na[q] = nb[q] = 0.0; }
+    for (int c = 0; c < NB; ++c) { fc[c] = 0.0; fn[c] = 0.0; if ((GL.mask >> c) & 1u) fc[c] = lds_ordered(base + 8 * c); }
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
         if (k + 1 < KS) {
 #pragma unroll
-            for (int q = 0; q < NBW; ++q) { na[q] = lds_ordered(Ar[q] + 4 * (k + 1) * DP); nb[q] = lds_ordered(Br[q] + 4 * (k + 1) * DP); }
+            for (int c = 0; c < NB; ++c) if ((GL.mask >> c) & 1u) fn[c] = lds_ordered(base + 8 * c + 4 * (k + 1) * DP);
         }
 #pragma unroll
-        for (int q = 0; q < NBW; ++q) dmma_ordered(acc[q][k & 1][0], acc[q][k & 1][1], fa[q], fb[q]);
+        for (int q = 0; q < GL.nb; ++q) dmma_ordered(acc[q][0], acc[q][1], fc[GL.rb[q]], fc[GL.cb[q]]);
 #pragma unroll
-        for (int q = 0; q < NBW; ++q) { fa[q] = na[q]; fb[q] = nb[q]; }
+        for (int c = 0; c < NB; ++c) fc[c] = fn[c];
     }
 #pragma unroll
-    for (int q = 0; q < NBW; ++q) {
-        const int rb = (code >> (6 * q)) & 7, cb = (code >> (6 * q + 3)) & 7;
-        if (mwarp + q * MW < G_.ntri)
-            *reinterpret_cast<double2*>(M + (8 * rb + g8) * DP + 8 * cb + 2 * t4) =
-                make_double2(acc[q][0][0] + acc[q][1][0], acc[q][0][1] + acc[q][1][1]);
+    for (int q = 0; q < GL.nb; ++q)
+        *reinterpret_cast<double2*>(M + (8 * GL.rb[q] + g8) * DP + 8 * GL.cb[q] + 2 * t4) = make_double2(acc[q][0], acc[q][1]);
+}
+template <int SN, int SMU, int W = 0>
+__device__ __forceinline__ void phase_gram5(double* M, const double* Ks, int mwarp, int lane) {
+    constexpr Eloc5Geom G_ = eloc5_geom(SN, SMU != 0);
+    if constexpr (W < G_.GWN) {
+        if (mwarp == W) phase_gram5w<SN, SMU, W>(M, Ks, lane);
+        else phase_gram5<SN, SMU, W + 1>(M, Ks, mwarp, lane);
     }
+}
+
+// Radial function and three derivatives from the certified Taylor table: nodes below `ncache` from the mirror in shared
+// memory (rows of kRtPitch doubles: the 16-byte chunks of eight different rows fall into different bank groups), the
+// others through L1.  One row = 96 bytes per item, different for every lane: from global memory that is up to 32 cache
+// lines per warp instruction, 29 % of the L1 / shared-memory data-pipe traffic of the sweep before the mirror.
+constexpr int kRtPitch = 14;
+__device__ __forceinline__ bool radial_eval_mirror(const RtHeader& T, const double* __restrict__ cache, int ncache, double d, double (&f)[4]) {
+    const double kf = rint(d * T.inv_delta);
+    if (T.coef == nullptr || !(kf < (double)T.n_nodes) || !(kf >= 0.0)) return false;
+    const double t = fma(-kf, T.delta, d);
+    const int k = (int)kf;
+    double c[kRtCoef];
+    if (k < ncache) {
+        const double2* c2 = reinterpret_cast<const double2*>(cache + k * kRtPitch);
+#pragma unroll
+        for (int q = 0; q < kRtCoef / 2; ++q) { const double2 v = c2[q]; c[2 * q] = v.x; c[2 * q + 1] = v.y; }
+    } else {
+        const double2* c2 = reinterpret_cast<const double2*>(T.coef + (size_t)k * kRtCoef);
+#pragma unroll
+        for (int q = 0; q < kRtCoef / 2; ++q) { const double2 v = __ldg(c2 + q); c[2 * q] = v.x; c[2 * q + 1] = v.y; }
+    }
+    double p0 = c[kRtDeg], p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+    for (int m = kRtDeg - 1; m >= 0; --m) {
+        p3 = fma(p3, t, p2); p2 = fma(p2, t, p1); p1 = fma(p1, t, p0); p0 = fma(p0, t, c[m]);
+    }
+    f[0] = p0; f[1] = p1; f[2] = 2.0 * p2; f[3] = 6.0 * p3;
+    return true;
 }
 
 #ifdef FF_E5_TIMING
@@ -138,12 +175,22 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
     const int NS = 4 * a.nsteps;
 
     for (int e = tid0; e < G_.total; e += NT) S[e] = 0.0;                             // zero padding of the matrices and vectors, once
+    // mirror of the head of the eta table (a.rt_cache_nodes rows fit behind the walker block)
+    double* const rt_cache = S + G_.total;
+    int ncache = 0;
+    {
+        const RtHeader he = rt_load_header(a.rt_eta);
+        if (he.coef != nullptr) ncache = min(a.rt_cache_nodes, he.n_nodes);
+        for (int e = tid0; e < ncache * kRtCoef; e += NT) {
+            const int k = e / kRtCoef, q = e - k * kRtCoef;
+            rt_cache[k * kRtPitch + q] = he.coef[e];
+        }
+    }
     __syncthreads();
 
     // Owners and workers run their own stage loops (the register allocation is the larger of the two, not their sum);
     // the CTA barriers inside are barrier 0 with all NT threads on both sides.
     if (owner0) {
-        const int gcode = gram5_code<SN, SMU>(max((tid0 >> 5) - G_.G0, 0));
         for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
             // ---- initial state: K = 1 (registers and shared copy), gDelta = 0; y = x -------------------------------
             double Kr[NB][2];
@@ -180,7 +227,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                 double* const Y = S + G_.oY;
                 double* const U = S + G_.oU;
                 // ======== phase 1: M = K^T K of this stage ==========================================================
-                if (warp >= G_.G0 && warp < G_.G0 + G_.GWN) phase_gram5<SN, SMU>(S + G_.oM, Ks, warp - G_.G0, stage_local(gcode), tid & 31);
+                if (warp >= G_.G0 && warp < G_.G0 + G_.GWN) phase_gram5<SN, SMU>(S + G_.oM, Ks, warp - G_.G0, tid & 31);
                 E5T(0);
                 named_bar_sync(0, NT);
                 E5T(1);
@@ -201,10 +248,12 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                                 if ((k & 3) == 0) s0 += v; else if ((k & 3) == 1) s1 += v; else if ((k & 3) == 2) s2 += v; else s3 += v;
                             }
                         } else {
-                            const double* Ar = A + a_row(2 * g1_i + (c8 == 7 ? 1 : 0)) * DP + (c8 >= 6 ? 1 : 0);
+                            // A is symmetric: block (al, be) of particle i is read down columns 2 i + al (consecutive
+                            // lanes: stride 2), rows 2 k + be (physical row a_row(2 k) + 4 be)
+                            const double* Ac = A + (c8 >= 6 ? 4 * DP : 0) + 2 * g1_i + (c8 == 7 ? 1 : 0);
 #pragma unroll
                             for (int k = 0; k < n; ++k) {
-                                const double v = (SMU != 0 || k != g1_i) ? Ar[2 * k] : 0.0;
+                                const double v = (SMU != 0 || k != g1_i) ? Ac[a_row(2 * k) * DP] : 0.0;
                                 if ((k & 3) == 0) s0 -= v; else if ((k & 3) == 1) s1 -= v; else if ((k & 3) == 2) s2 -= v; else s3 -= v;
                             }
                         }
@@ -368,7 +417,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                             Rii[0] = v0; Rii[RMAT] = v1; Rii[2 * RMAT] = v2; Rii[3 * RMAT] = v3; Rii[4 * RMAT] = v4;
                             const int i2 = 2 * it_i;
                             *reinterpret_cast<double2*>(A + a_row(i2) * DP + i2) = make_double2(-a00, -a01);
-                            A[a_row(i2 + 1) * DP + i2 + 1] = -a11;
+                            *reinterpret_cast<double2*>(A + a_row(i2 + 1) * DP + i2) = make_double2(-a01, -a11);
                         }
                     }
                     E5T(0);
@@ -458,7 +507,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                     inv_d = rsqrt(d2);
                     dd = d2 * inv_d;
                     double f[4];
-                    if (!radial_table_eval<3>(my_rt, dd, f))
+                    if (!radial_eval_mirror(my_rt, rt_cache, it_pair ? ncache : 0, dd, f))
                         radial_direct_global(it_pair ? a.eta_w1 : a.mu_w1, it_pair ? a.eta_b1 : a.mu_b1,
                                              it_pair ? a.eta_w2 : a.mu_w2, it_pair ? a.H_eta : a.H_mu, dd, f);
                     f0 = f[0]; f1 = f[1]; f2 = f[2]; f3 = f[3];
