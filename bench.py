@@ -96,8 +96,10 @@ def flops_per_walker_eloc(n, H_eta, H_mu, ode_steps, tables=True):
 
 
 def hbm_bytes_per_walker_eloc(n, has_mu, ode_steps):
+    """coordinates in, adjoint stash out (stage inputs + three radial values per item), results out, and the final
+    state of the sweep (y, L, gDelta, Delta, lapDelta, J) written once and read once by the finale kernel"""
     D, P = 2 * n, n * (n - 1) // 2 + (n if has_mu else 0)
-    return 8 * (D + 4 * ode_steps * (D + 3 * P) + 2 * D + 6)
+    return 8 * (D + 4 * ode_steps * (D + 3 * P) + 2 * D + 6 + 2 * (3 * D + 2 + D * D))
 
 
 def build_model(args, dev):
@@ -265,13 +267,14 @@ def run_ours(args):
         "gpu_launches": int(launches),     # counted by the library (ff_launch_count) over the timed steps of this rank
         "clocks": sampler.summary(),
         "breakdown_ms": {k: round(v, 2) for k, v in bd.items()},
-        "roofline": {"bound": "fp64", "kernel": "ff::eloc2_kernel<20,1> (E_loc sweep)", "achieved": fl / (eloc_ms * 1e-3) / 1e12,
+        "roofline": {"bound": "fp64", "kernel": "ff_eloc: ff::eloc5_kernel<20,1> (E_loc sweep, 92 % of the call) + ff::eloc_finale_kernel + table build", "achieved": fl / (eloc_ms * 1e-3) / 1e12,
                      "peak": peak.value / 1e12, "unit": "TFLOP/s", "frac": fl / (eloc_ms * 1e-3) / peak.value,
                      "peak_source": "ff_fp64_peak DFMA microbenchmark on this device (MEASURED_PEAKS.json has no fp64 entry)",
                      "flops_counted": "executed formulation (radial functions from certified Taylor tables)" if tables_on
                                       else "reference formulation (every hidden unit evaluated)",
-                     # ncu --set full (profiles/r01_eloc_ncu_full.md): 3.211 GB written + 0.021 GB read for 9472 walkers
-                     "traffic": 3.2323e9 / 9472 * B if (n == 20 and args.hidden == 50 and args.ode_steps == 16) else None,
+                     # ncu --set full (profiles/r02_eloc5_ncu_full.md): sweep 3.326 GB written + 0.005 GB read, finale
+                     # 0.134 GB read + 0.005 GB written for 9472 walkers
+                     "traffic": 3.4704e9 / 9472 * B if (n == 20 and args.hidden == 50 and args.ode_steps == 16) else None,
                      "traffic_source": "ncu dram__bytes_read+write, 9472-walker capture scaled per walker",
                      "kernel_ms": eloc_ms,
                      "hbm": {"achieved": by / (eloc_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

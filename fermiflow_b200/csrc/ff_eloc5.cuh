@@ -12,8 +12,7 @@
 //   * Two CTA barriers per RK stage, and both kinds of warps have work in both phases:
 //       phase 1   workers: finish the items of the stage from (r and the radial functions) kept in registers -- matrices R_c of the
 //                 per-particle sums, off-diagonal blocks of A = dv/dy, stash.
-//                 owners: M = K^T K on the tensor cores from the shared copy of K (owners 1..3 at NB = 5, so that every
-//                 scheduler sees 100 DMMA per stage: owners 0 and 4 share one and have the larger part of K A).
+//                 owners: M = K^T K on the tensor cores from the shared copy of K.
 //       phase 2   owners: row sums (k_y: y advances; u, rho, diagonal of A), K A on the tensor cores, K u, RK update of
 //                 K in registers, shared copy of the new K.
 //                 workers: contractions of their items with M, per-particle sums of those, A L, RK update of L, Delta,
@@ -37,8 +36,8 @@ __host__ __device__ constexpr Eloc5Geom eloc5_geom(int n, bool has_mu) {
     g.NP = n * (n - 1) / 2; g.P = g.NP + (has_mu ? n : 0);
     g.NB = g.D8 / 8; g.ntri = g.NB * (g.NB + 1) / 2; g.MAT = g.D8 * g.DP;
     g.OW = g.NB; g.WW = (g.P + 31) / 32; g.threads = 32 * (g.OW + g.WW);
-    // owner warps that form the Gram matrix in phase 1
-    g.G0 = g.NB >= 5 ? 1 : 0; g.GWN = g.NB >= 5 ? 3 : g.NB;
+    // owner warps that form the Gram matrix in phase 1 (all of them)
+    g.G0 = 0; g.GWN = g.NB < g.ntri ? g.NB : g.ntri;
     g.RP = n | 1; g.RMAT = n * g.RP;
     int off = 0;
     g.oKs = off; off += g.MAT;
@@ -62,18 +61,16 @@ __host__ __device__ constexpr bool eloc5_supported(int n, bool has_mu) {
            (g.ntri + g.GWN - 1) / g.GWN <= 5 && g.threads <= 384;
 }
 
-// Blocks of the upper block triangle of M = K^T K that Gram warp W of MW forms.  NB = 5, MW = 3: block rows {0}, {1, 4},
-// {2, 3} -- five blocks each, and the warps need only 5 / 4 / 3 distinct operand fragments per k-step.
+// Blocks of the upper block triangle of M = K^T K that Gram warp W of MW forms.  NB = 5, MW = 5: three blocks each, chosen
+// so that a warp needs only 2 or 3 distinct operand fragments per k-step (14 fetches per k-step in total for 15 products).
 struct GramList { int nb; int rb[5]; int cb[5]; unsigned mask; };
 __host__ __device__ constexpr GramList gram_list(int NB, int MW, int W) {
     GramList L{};
-    if (NB == 5 && MW == 3) {
-        const int rows[3][2] = {{0, -1}, {1, 4}, {2, 3}};
-        for (int t = 0; t < 2; ++t) {
-            const int r = rows[W][t];
-            if (r < 0) continue;
-            for (int c = r; c < NB; ++c) { L.rb[L.nb] = r; L.cb[L.nb] = c; ++L.nb; }
-        }
+    if (NB == 5 && MW == 5) {
+        const int blocks[5][3][2] = {{{0, 0}, {0, 1}, {0, 2}}, {{0, 3}, {0, 4}, {3, 4}}, {{1, 1}, {1, 2}, {2, 2}},
+                                     {{1, 3}, {1, 4}, {3, 3}}, {{2, 3}, {2, 4}, {4, 4}}};
+        for (int t = 0; t < 3; ++t) { L.rb[t] = blocks[W][t][0]; L.cb[t] = blocks[W][t][1]; }
+        L.nb = 3;
     } else {
         int blk = 0;
         for (int r = 0; r < NB; ++r)

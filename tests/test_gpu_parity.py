@@ -510,13 +510,14 @@ def test_flow_kernel_variants_agree_full_size(dev):
 
 @pytest.mark.parametrize("B", [1, 2, 297, 1500])
 def test_eloc_kernel_variants_agree_full_size(dev, B):
-    """N = 20: the statically specialised sweep (default) against the generic flow_kernel<MODE_ELOC>
-    (option eloc_generic), with the Taylor tables and with direct evaluation of every hidden unit (no_table)."""
+    """N = 20: the default sweep (eloc5_kernel: register-resident Jacobian, specialised warps) against the generic
+    flow_kernel<MODE_ELOC> (option eloc_generic), with the Taylor tables and with direct evaluation of every hidden unit
+    (no_table: eloc2_kernel), against its predecessors (eloc_v4, eloc_v2) and without the table mirror (no_rt_cache)."""
     model = _n20_model(dev, nsteps=4)
     _, x = model.sample((B,))
     res = []
     for env in (dict(eloc_generic=0, no_table=0), dict(eloc_generic=1, no_table=0), dict(eloc_generic=0, no_table=1),
-                dict(eloc_generic=1, no_table=1)):
+                dict(eloc_generic=1, no_table=1), dict(eloc_v4=1), dict(eloc_v2=1), dict(no_rt_cache=1)):
         with _opts(**env):
             res.append(model.local_energy(x, stash=True))
     for r in res[1:]:
