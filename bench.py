@@ -47,6 +47,12 @@ def parse():
                    help="walkers per step of the CPU reference arm (a second, 4x smaller batch is timed beside it so "
                         "that the saturation of the CPU throughput with the batch is visible)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--config", default="n20", choices=["n20", "readme_finiteT", "strong_coupling", "slater_sweep"],
+                   help="n20 (default; BASELINE configs[2], the configuration the metric is quoted on) | readme_finiteT "
+                        "(configs[1]: beta 10, 3 up, Z 2, deltaE 2, Boltzmann sampler, 8000 walkers) | strong_coupling "
+                        "(configs[3]: Z 8, N 12, 32 RK4 steps, finite T) | slater_sweep (configs[4]: log|det| + gradient + "
+                        "Laplacian, N = 6..30, 1e6 walkers).  The extra configurations print the same JSON shape; the driver "
+                        "runs the default only.")
     return p.parse_args()
 
 
@@ -289,6 +295,209 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+FINITE_T = {   # BASELINE.json configs[1] and configs[3] (reference: src/BetaFermionHO2D.py command lines)
+    "readme_finiteT": dict(beta=10.0, nup=3, ndown=0, Z=2.0, deltaE=2.0, nsteps=16, batch=8000,
+                           what="README finite-T run (--beta 10.0 --nup 3 --Z 2.0 --deltaE 2.0 --boltzmann)"),
+    "strong_coupling": dict(beta=2.0, nup=12, ndown=0, Z=8.0, deltaE=2.0, nsteps=32, batch=8000,
+                            what="strong-coupling Wigner-molecule regime (--beta 2.0 --nup 12 --Z 8.0 --deltaE 2.0 --boltzmann, 32 RK4 steps)"),
+}
+
+
+def run_config(args):
+    """The other BASELINE configurations on one GPU, same JSON shape as the default line (device-timed value, end-to-end
+    value through host buffers, roofline of the dominant kernel, CPU baseline of the reference algorithm)."""
+    import ctypes as C
+    from fermiflow_b200 import _lib as L
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    peak = C.c_double()
+    L.check(L.lib().ff_fp64_peak(20000, C.byref(peak), None))
+    sampler = ClockSampler(0)
+    if args.config == "slater_sweep":
+        return run_slater_sweep(args, dev, peak.value, sampler)
+    from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, BetaVMC, HO, CoulombPairPotential
+    from fermiflow_b200 import utils as U
+    import fermiflow_b200.VMC as V
+    cfg = FINITE_T[args.config]
+    n = cfg["nup"] + cfg["ndown"]
+    g = torch.Generator().manual_seed(42)
+    eta, mu = MLP(1, args.hidden), MLP(1, args.hidden)
+    with torch.no_grad():
+        for m in (eta, mu):
+            m.fc1.weight.copy_(torch.randn(m.fc1.weight.shape, generator=g))
+            m.fc1.bias.copy_(torch.randn(m.fc1.bias.shape, generator=g))
+            m.fc2.weight.copy_(1e-2 * torch.randn(m.fc2.weight.shape, generator=g))
+    cnf = CNF(Backflow(eta, mu=mu), (0.0, 1.0), nsteps=cfg["nsteps"])
+    model = BetaVMC(cfg["beta"], cfg["nup"], cfg["ndown"], cfg["deltaE"], True, HO2D(), FreeFermion(dev), cnf,
+                    CoulombPairPotential(cfg["Z"]), sp_potential=HO()).to(dev)
+    model.basedist.manual_seed(1000)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    B = cfg["batch"]
+    params = list(model.parameters())
+    nparam = sum(p.numel() for p in params)
+    eloc_events = []
+    orig_sweep = U.eloc_sweep
+
+    def timed_sweep(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); r = orig_sweep(*a, **k); e1.record()
+        eloc_events.append((e0, e1))
+        return r
+    V.eloc_sweep = timed_sweep
+
+    def step():
+        gphi, gtheta = model(B)
+        opt.zero_grad(set_to_none=True)
+        gphi.backward(); gtheta.backward()
+        opt.step()
+
+    steps, warmup = max(args.steps, 20), max(args.warmup, 5)
+    for _ in range(warmup):
+        step()
+    eloc_events.clear()
+    launches0 = L.lib().ff_launch_count()
+    sampler.start()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step()
+    t1.record(); torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    launches = L.lib().ff_launch_count() - launches0
+    eloc_ms = sum(a.elapsed_time(b) for a, b in eloc_events) / max(len(eloc_events), 1)
+    host_params = torch.cat([p.detach().reshape(-1) for p in params]).cpu().pin_memory()
+    host_out = torch.empty(nparam + 5, dtype=torch.float64).pin_memory()
+    dev_params = torch.empty(nparam, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        dev_params.copy_(host_params, non_blocking=True)
+        o = 0
+        with torch.no_grad():
+            for p in params:
+                p.copy_(dev_params[o:o + p.numel()].view_as(p)); o += p.numel()
+        gphi, gtheta = model(B)
+        opt.zero_grad(set_to_none=True)
+        gphi.backward(); gtheta.backward()
+        obs = torch.stack([getattr(model, "_obs_dev")[k].reshape(()) for k in ("E", "E_std", "F", "F_std", "S")])
+        host_out.copy_(torch.cat([p.grad.reshape(-1) for p in params] + [obs]), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record(); torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    fl = flops_per_walker_eloc(n, args.hidden, args.hidden, cfg["nsteps"], tables=L.get_option("no_table") == 0) * B
+    line = {
+        "metric": "VMC walker-updates/s (sample+E_loc+grad), " + args.config, "value": B * steps / (ms * 1e-3), "unit": UNIT,
+        "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: N=%d, %d many-body states, %d walkers per iteration, Deta=Dmu=%d, %d RK4 steps" % (
+            cfg["what"], n, model.Nstates, B, args.hidden, cfg["nsteps"]), "walkers_total": B, "ode_steps": cfg["nsteps"],
+            "l2_policy": "inputs smaller than L2 (8000 walkers); every iteration writes and reads its own adjoint stash (%.2f GB)" % (
+                hbm_bytes_per_walker_eloc(n, True, cfg["nsteps"]) * B / 1e9)},
+        "e2e": {"value": B * steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nparam * 8, "d2h_bytes_per_step": (nparam + 5) * 8},
+        "gpu_launches": int(launches), "clocks": sampler.summary(),
+        "roofline": {"bound": "fp64", "kernel": "ff_eloc (E_loc sweep of the %d-particle block)" % n, "achieved": fl / (eloc_ms * 1e-3) / 1e12,
+                     "peak": peak.value / 1e12, "unit": "TFLOP/s", "frac": fl / (eloc_ms * 1e-3) / peak.value,
+                     "peak_source": "ff_fp64_peak DFMA microbenchmark on this device", "traffic": None, "kernel_ms": eloc_ms},
+        "F": model.F, "F_std": model.F_std, "E": model.E, "S": model.S,
+    }
+    if not args.no_cpu_baseline:
+        # the reference algorithm at the same particle number on the host cores (ground-state occupation for every walker:
+        # the per-walker cost of the multi-state Slater determinant is the same)
+        from oracle import reference_port as R
+        torch.set_num_threads(os.cpu_count() or 1)
+        R.time_vmc_iteration(cfg["nup"], cfg["ndown"], args.hidden, cfg["Z"], 1, seed=1, equil=2)
+        w = 16 if n > 6 else 64
+        t = R.time_vmc_iteration(cfg["nup"], cfg["ndown"], args.hidden, cfg["Z"], w, seed=7)
+        line["cpu_baseline"] = {"value": w / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "ref_walkers": w,
+                                "sample": "1 VMC iteration of %d walkers of the %s (ground-state occupation for every walker)" % (w, _ref_note(n))}
+    print(json.dumps(line))
+
+
+def run_slater_sweep(args, dev, peak, sampler):
+    """BASELINE configs[4]: batched log|det| + gradient + exact Laplacian of the free-fermion state, N = 6..30 (N/2 up, N/2
+    down), 1e6 walkers, against the reference's autograd path (slogdet + 1 + 2N nested passes, utils.py:44-65) on the host."""
+    from fermiflow_b200 import HO2D, FreeFermion, _lib as L
+    from oracle import fermiflow_oracle as O
+    B, cpu_walkers = 1000000, 4096
+    ho, ffm = HO2D(), FreeFermion(dev)
+    torch.set_num_threads(os.cpu_count() or 1)
+    rows = []
+    sampler.start()
+    launches0 = L.lib().ff_launch_count()
+    for N in range(6, 31, 2):
+        nup = N // 2
+        up, dn = ho.orbitals[:nup], ho.orbitals[:N - nup]
+        x = 1.2 * torch.randn(B, N, 2, device=dev)
+        xh = x.cpu().pin_memory()
+        for _ in range(3):
+            ffm.log_prob_grad_laplacian(up, dn, x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for _ in range(5):
+            e0.record(); logp, grad, lap = ffm.log_prob_grad_laplacian(up, dn, x); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]
+        # end to end: coordinates from pinned host memory, log p / gradient / Laplacian back to the host
+        out_h = [torch.empty_like(t, device="cpu").pin_memory() for t in (logp, grad, lap)]
+        e0.record()
+        xd = xh.to(dev, non_blocking=True)
+        res = ffm.log_prob_grad_laplacian(up, dn, xd)
+        for o, r in zip(out_h, res):
+            o.copy_(r, non_blocking=True)
+        e1.record(); torch.cuda.synchronize()
+        e2e_ms = e0.elapsed_time(e1)
+        row = {"N": N, "gpu_ms": round(ms, 3), "walkers_per_s": B / ms * 1e3, "e2e_walkers_per_s": B / e2e_ms * 1e3}
+        if not args.no_cpu_baseline:
+            xc = x[:cpu_walkers].cpu()
+            O.free_fermion_grad_laplacian(list(range(nup)), list(range(N - nup)), xc[:64])      # warm-up
+            t = time.time()
+            lp_ref, g_ref, l_ref = O.free_fermion_grad_laplacian(list(range(nup)), list(range(N - nup)), xc)
+            tc = time.time() - t
+            row["cpu_walkers_per_s"] = cpu_walkers / tc
+            row["max_rel_err_vs_oracle"] = max(float((logp[:cpu_walkers].cpu() - lp_ref).abs().max() / lp_ref.abs().max()),
+                                               float((grad[:cpu_walkers].cpu() - g_ref).abs().max() / g_ref.abs().max()),
+                                               float((lap[:cpu_walkers].cpu() - l_ref).abs().max() / l_ref.abs().max()))
+        rows.append(row)
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    r20 = [r for r in rows if r["N"] == 20][0]
+    ns = 10
+    # executed flops per walker at N = 20 (two 10 x 10 blocks): Gauss-Jordan on [Phi | I] 2 ns^2 (2 ns) + orbitals and the
+    # Jacobi-formula contractions 8 ns^2 + 1D oscillator tables 2 ns * 8 * 10
+    fl = 2 * (2 * ns * ns * 2 * ns + 8 * ns * ns + 2 * ns * 80)
+    hbm = (20 * 2 + 20 * 2 + 2) * 8.0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    line = {
+        "metric": "batched log|det| + gradient + exact Laplacian, walkers/s at N=20 (sweep N=6..30)", "value": r20["walkers_per_s"],
+        "unit": "walkers/s", "n_gpus": 1, "steps": 5, "warmup": 3, "ms_per_step": r20["gpu_ms"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "kernel microbench: free-fermion log|det| + gradient + Laplacian, N = 6..30 (N/2 up, N/2 down), 1e6 walkers",
+                   "walkers_total": B, "l2_policy": "inputs larger than L2 from N = 8 on (16 N bytes in, 16 N + 16 out per walker)"},
+        "e2e": {"value": r20["e2e_walkers_per_s"], "unit": "walkers/s", "h2d_bytes_per_step": B * 40 * 8, "d2h_bytes_per_step": B * 42 * 8},
+        "gpu_launches": int(L.lib().ff_launch_count() - launches0), "clocks": sampler.summary(),
+        "roofline": {"bound": "fp64", "kernel": "ff::slater_warp_kernel (one warp per walker)", "achieved": fl * r20["walkers_per_s"] / 1e12,
+                     "peak": peak / 1e12, "unit": "TFLOP/s", "frac": fl * r20["walkers_per_s"] / peak, "traffic": None,
+                     "peak_source": "ff_fp64_peak DFMA microbenchmark on this device",
+                     "hbm": {"achieved": hbm * r20["walkers_per_s"] / 1e9, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
+                             "frac": hbm * r20["walkers_per_s"] / 1e9 / peaks.get("hbm_gbs", 6650.0)},
+                     "note": "latency / issue bound: shuffle-based pivot search and rank-1 updates of 10 x 21 matrices"},
+        "sweep": rows,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = {"value": r20["cpu_walkers_per_s"], "unit": "walkers/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "%d walkers per N through the reference's path (torch slogdet + 1 + 2N nested autograd passes, "
+                                          "oracle/fermiflow_oracle.py free_fermion_grad_laplacian), one warm-up call" % cpu_walkers}
+    print(json.dumps(line))
+
+
 def _ref_note(n):
     return ("reference algorithm ported to torch-CPU (oracle/reference_port.py: dopri5 rtol 1e-6 + continuous adjoint + "
             "2N nested autograd passes, N=%d); /root/reference is plain Python and needs the absent torchdiffeq" % n)
@@ -359,5 +568,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
-    else:
+    elif a.config == "n20":
         run_ours(a)
+    else:
+        run_config(a)

@@ -42,27 +42,74 @@ def test_finite_temperature_readme_run(dev):
     assert sum(F[-3:]) / 3 < sum(F[:3]) / 3 - 0.02
 
 
-def test_energy_statistically_consistent_with_reference_algorithm(dev):
-    """Same parameters, independent walkers: E from the CUDA path (16384 walkers, fixed-step
-    flow) vs E from the reference's own algorithm on the CPU (adaptive solver + adjoint,
-    96 walkers); they must agree within 4 standard errors."""
-    from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
-    from oracle import reference_port as R
-    params = R.make_params(8, 5, scale=5e-2)
+def _flow_from_port_params(params, hidden, nsteps, dev):
+    from fermiflow_b200 import MLP, Backflow, CNF
     mods = []
     for k in range(2):
-        m = MLP(1, 8)
+        m = MLP(1, hidden)
         with torch.no_grad():
             m.fc1.weight.copy_(params[3 * k][:, None]); m.fc1.bias.copy_(params[3 * k + 1]); m.fc2.weight.copy_(params[3 * k + 2][None])
         mods.append(m)
-    cnf = CNF(Backflow(mods[0], mu=mods[1]), (0.0, 1.0), nsteps=16)
-    model = GSVMC(2, 2, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(2.0), sp_potential=HO()).to(dev)
+    return CNF(Backflow(mods[0], mu=mods[1]), (0.0, 1.0), nsteps=nsteps)
+
+
+@pytest.mark.parametrize("nup,ndown,scale,cpu_walkers", [(2, 2, 5e-2, 96), (3, 3, 2e-2, 48)])
+def test_energy_statistically_consistent_with_reference_algorithm(dev, nup, ndown, scale, cpu_walkers):
+    """Same parameters, independent walkers: E from the CUDA path (16384 walkers, fixed-step flow) vs E from the
+    reference's own algorithm on the CPU (Metropolis, adaptive dopri5 + adjoint, 1 + 2N nested autograd passes);
+    they must agree within 4 standard errors.  (3, 3) at Z = 2 is BASELINE configs[0], the reference's own
+    CPU-runnable case src/FermionHO2D.py N = 6."""
+    from fermiflow_b200 import HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
+    from oracle import reference_port as R
+    params = R.make_params(8, 5, scale=scale)
+    cnf = _flow_from_port_params(params, 8, 16, dev)
+    model = GSVMC(nup, ndown, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(2.0), sp_potential=HO()).to(dev)
     model(16384)
     e_gpu, se_gpu = model.E, model.E_std / math.sqrt(16384)
     torch.manual_seed(3)
-    E, E_std, _ = R.vmc_iteration(2, 2, params, True, 2.0, 96)
-    se_ref = E_std / math.sqrt(96)
+    E, E_std, _ = R.vmc_iteration(nup, ndown, params, True, 2.0, cpu_walkers)
+    se_ref = E_std / math.sqrt(cpu_walkers)
     assert abs(e_gpu - E) < 4.0 * math.hypot(se_gpu, se_ref), (e_gpu, se_gpu, E, se_ref)
+    # the two estimates of the spread of E_loc describe the same distribution
+    assert 0.5 < model.E_std / E_std < 2.0, (model.E_std, E_std)
+
+
+def test_readme_finite_temperature_estimators_consistent_with_reference_algorithm(dev):
+    """BASELINE configs[1] (README: --beta 10.0 --nup 3 --Z 2.0 --deltaE 2.0 --boltzmann): F, E and S of the CUDA path
+    (BetaVMC.forward, 16384 independent walkers) against the reference's own algorithm on the CPU -- occupations drawn
+    from the same Boltzmann weights (VMC.py:94-97), Metropolis on every occupation's |det|^2, adaptive dopri5 flow,
+    log p through the adjoint, 1 + 2N nested autograd passes, estimators of VMC.py:139-171 -- within 4 standard errors."""
+    from fermiflow_b200 import HO2D, FreeFermion, BetaVMC, HO, CoulombPairPotential
+    from oracle import reference_port as R, fermiflow_oracle as O
+    beta, nup, Z, deltaE, B_cpu = 10.0, 3, 2.0, 2.0, 64
+    params = R.make_params(8, 11, scale=3e-2)
+    cnf = _flow_from_port_params(params, 8, 16, dev)
+    model = BetaVMC(beta, nup, 0, deltaE, True, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(Z), sp_potential=HO()).to(dev)
+    model(16384)
+    n_gpu = 16384
+    # CPU: the reference algorithm
+    torch.manual_seed(5)
+    states, Es = O.fermion_states(nup, 0, deltaE)
+    assert len(states) == model.Nstates
+    logits = O.boltzmann_logits(beta, Es)
+    idx = torch.sort(torch.multinomial(torch.softmax(logits, -1), B_cpu, replacement=True))[0]
+    eloc = torch.empty(B_cpu)
+    ts = (0.0, 1.0)
+    for st in torch.unique(idx):
+        sel = idx == st
+        orb = list(states[int(st)])
+        z = R.metropolis(orb, [], int(sel.sum()))
+        x = R.generate(z, params, True, ts).detach().requires_grad_(True)
+        _, g, lap = R.y_grad_laplacian(lambda t: R.logp(t, orb, [], params, True, ts, False), x)
+        kin = -0.25 * lap - 0.125 * (g ** 2).sum(dim=(-2, -1))
+        eloc[sel] = (kin + O.potential_coulomb(x, Z) + O.potential_ho(x)).detach()
+    est = O.beta_vmc_estimators(eloc, idx, logits, beta)
+    for k in ("E", "F"):
+        se = math.hypot(getattr(model, k + "_std") / math.sqrt(n_gpu), est[k + "_std"] / math.sqrt(B_cpu))
+        assert abs(getattr(model, k) - est[k]) < 4.0 * se, (k, getattr(model, k), est[k], se)
+    # at beta = 10 the excited occupations carry e^-10 of the weight: both entropies vanish to that order
+    assert abs(model.S_analytical - est["S_analytical"]) < 1e-12
+    assert abs(model.S - est["S"]) < 0.02
 
 
 def test_strong_coupling_finite_temperature_run(dev):
