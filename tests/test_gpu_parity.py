@@ -554,13 +554,15 @@ def test_metropolis_kernels_bit_identical(dev, nup, ndn):
     from fermiflow_b200 import HO2D, FreeFermion
     ho = HO2D()
     outs = []
-    for env in (dict(metropolis_kernel=2), dict(metropolis_kernel=3), dict(metropolis_kernel=1)):
+    for env in (dict(metropolis_kernel=2), dict(metropolis_kernel=3), dict(metropolis_kernel=1),
+                dict(metropolis_kernel=1, metropolis_no_split=1)):
         with _opts(**env):
             ff = FreeFermion(dev)
             ff.manual_seed(77)
             outs.append(ff.sample(ho.orbitals[:nup], ho.orbitals[:ndn], (1000,), equilibrim_steps=40))
     assert torch.equal(outs[0], outs[1])
-    assert torch.equal(outs[0], outs[2])      # register-resident sampler (ff_metro_reg.cuh)
+    assert torch.equal(outs[0], outs[2])      # register-resident sampler (ff_metro_reg.cuh), one thread per spin block
+    assert torch.equal(outs[0], outs[3])      # ... and one thread per walker
     assert torch.isfinite(outs[0]).all()
 
 
