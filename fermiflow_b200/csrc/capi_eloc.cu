@@ -48,9 +48,37 @@ int plan_finale(ff::FlowArgs& a, int W) {
     return 2 * ((NP + 7) / 8) + 2 + W * a.wstride;          // doubles of dynamic shared memory
 }
 
-// Finale kernel from the final states in global memory (fin: `stride` doubles per walker).
+// Finale from the final states in global memory (fin: `stride` doubles per walker): one warp per walker
+// (ff_finale.cuh); option "finale_cta" or an unusual particle number: the CTA-synchronous eloc_finale_kernel.
+template <int NB8>
+int launch_finale_warp(const ff::FlowArgs& a, const double* fin, int stride, cudaStream_t st) {
+    const DevInfo di = dev_info();
+    const int warps = 4;
+    const size_t smem = (size_t)warps * ff::finale_warp_slice(a.n, std::max(a.n_up, a.n - a.n_up)) * 8;
+    auto kernel = ff::eloc_finale_warp_kernel<NB8>;
+    if ((long long)smem > di.smem_optin) return FF_FALLBACK;
+    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * warps, smem));
+    if (occ < 1) return FF_FALLBACK;
+    const long long grid = std::min<long long>((a.B + warps - 1) / warps, (long long)di.sms * occ);
+    kernel<<<(unsigned)grid, 32 * warps, smem, st>>>(a, fin, stride);
+    FF_LAUNCHED();
+    return 0;
+}
+
 int launch_finale(const ff::FlowArgs& a, const double* fin, int stride, cudaStream_t st) {
     const DevInfo di = dev_info();
+    if (!opt(OPT_FINALE_CTA)) {
+        int r = FF_FALLBACK;
+        switch ((2 * a.n + 7) / 8) {
+            case 2: r = launch_finale_warp<2>(a, fin, stride, st); break;
+            case 3: r = launch_finale_warp<3>(a, fin, stride, st); break;
+            case 5: r = launch_finale_warp<5>(a, fin, stride, st); break;
+            default: break;
+        }
+        if (r != FF_FALLBACK) return r;
+    }
     ff::FlowArgs f = a;
     int W = 2;
     size_t fsmem = (size_t)plan_finale(f, W) * 8;

@@ -244,6 +244,19 @@ __device__ __forceinline__ void hermite_values(double x, double (&v)[8]) {
     }
 }
 
+// three-term recursion of the normalised 1D oscillator functions (orbitals.py:66-90): tabulated square roots
+static __constant__ double c_herm_up[8] = {   // sqrt(2 / (k + 1))
+    1.4142135623730951, 1.0, 0.8164965809277260, 0.7071067811865476, 0.6324555320336759,
+    0.5773502691896257, 0.5345224838248488, 0.5};
+static __constant__ double c_herm_dn[8] = {   // sqrt(k / (k + 1))
+    0.0, 0.7071067811865476, 0.8164965809277260, 0.8660254037844386, 0.8944271909999159,
+    0.9128709291752769, 0.9258200997725514, 0.9354143466934853};
+static __constant__ double c_herm_d1[8] = {   // sqrt(2 a)
+    0.0, 1.4142135623730951, 2.0, 2.4494897427831779, 2.8284271247461903, 3.1622776601683795,
+    3.4641016151377544, 3.7416573867739413};
+
+constexpr int kHermStride = 49;             // doubles per particle in the 1D table (psi, psi', psi'' of 8 orders, two coordinates; odd: no bank conflicts)
+
 static __constant__ unsigned char c_orb_nx[kMaxOrb] = {
     0, 0,1, 0,1,2, 0,1,2,3, 0,1,2,3,4, 0,1,2,3,4,5, 0,1,2,3,4,5,6, 0,1,2,3,4,5,6,7};
 static __constant__ unsigned char c_orb_ny[kMaxOrb] = {

@@ -26,6 +26,7 @@
 //     occupancy (eloc_finale_kernel) from the final state written to global memory (14 KB per walker).
 #pragma once
 #include "ff_eloc2.cuh"
+#include "ff_finale.cuh"
 
 namespace ff {
 

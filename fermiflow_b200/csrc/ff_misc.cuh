@@ -171,18 +171,7 @@ __global__ void __launch_bounds__(256) slater_kernel(const SlaterArgs a) {
 // Replaces slater.py:4-68 / 70-156 forward + backward and the 2N autograd passes of
 // utils.py:44-65 for f = FreeFermion.log_prob.
 // ---------------------------------------------------------------------------------------
-static __constant__ double c_herm_up[8] = {   // sqrt(2 / (k + 1))
-    1.4142135623730951, 1.0, 0.8164965809277260, 0.7071067811865476, 0.6324555320336759,
-    0.5773502691896257, 0.5345224838248488, 0.5};
-static __constant__ double c_herm_dn[8] = {   // sqrt(k / (k + 1))
-    0.0, 0.7071067811865476, 0.8164965809277260, 0.8660254037844386, 0.8944271909999159,
-    0.9128709291752769, 0.9258200997725514, 0.9354143466934853};
-static __constant__ double c_herm_d1[8] = {   // sqrt(2 a)
-    0.0, 1.4142135623730951, 2.0, 2.4494897427831779, 2.8284271247461903, 3.1622776601683795,
-    3.4641016151377544, 3.7416573867739413};
-
 constexpr int kSlaterWarpMax = 16;          // particles per spin block
-constexpr int kHermStride = 49;             // doubles per particle in the 1D table (odd: no bank conflicts)
 __host__ __device__ inline int slater_warp_slice(int nmax) {      // doubles of shared memory per warp
     return ff_even(nmax * (2 * nmax + 1) + nmax * kHermStride + 2);
 }

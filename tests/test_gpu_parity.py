@@ -517,7 +517,7 @@ def test_eloc_kernel_variants_agree_full_size(dev, B):
     _, x = model.sample((B,))
     res = []
     for env in (dict(eloc_generic=0, no_table=0), dict(eloc_generic=1, no_table=0), dict(eloc_generic=0, no_table=1),
-                dict(eloc_generic=1, no_table=1), dict(eloc_v4=1), dict(eloc_v2=1), dict(no_rt_cache=1)):
+                dict(eloc_generic=1, no_table=1), dict(eloc_v4=1), dict(eloc_v2=1), dict(no_rt_cache=1), dict(finale_cta=1)):
         with _opts(**env):
             res.append(model.local_energy(x, stash=True))
     for r in res[1:]:
