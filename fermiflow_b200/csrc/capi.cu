@@ -153,5 +153,14 @@ int ff_cnf_delta_logp(const ff_model* m, const double* x, long long B, double* z
 }
 
 #include "capi_rest.inc"
+#ifdef FF_PG_TIMING
+extern "C" int ff_debug_pg_cycles(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, ff::g_pg_cyc, sizeof(unsigned long long) * 160);
+    cudaMemcpyFromSymbol(out + 160, ff::g_pg_maxbin, sizeof(unsigned long long) * 4);
+    if (reset) { unsigned long long z[160] = {}; cudaMemcpyToSymbol(ff::g_pg_cyc, z, sizeof z); cudaMemcpyToSymbol(ff::g_pg_maxbin, z, 32); }
+    return 0;
+}
+#endif
 
 }  // extern "C"

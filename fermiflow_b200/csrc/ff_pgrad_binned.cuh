@@ -122,13 +122,36 @@ __global__ void __launch_bounds__(256) pgrad_bins_setup_kernel(const PGradBinArg
         }
         const double nbe_min = ceil(range / de_max) + 1.0;
         const bool ok = !far && isfinite(wmx[0]) && isfinite(wmx[1]) && nbm + nbe_min <= (double)kPgMaxBins;
-        const double nbe = ok ? (double)kPgMaxBins - nbm : nbe_min;
-        const double de = ok ? range / (nbe - 1.0) : de_max;
+        // mu: no particle is farther from the centre than the largest pair distance, so its nodes cover
+        // [0, min(kPgDmaxMu, range)] (beyond: direct sums, as for eta) at HALF the admissible spacing.  The radial
+        // distribution of the dot is peaked (shells): with the coarsest admissible nodes over [0, kPgDmaxMu] the hottest mu
+        // bins of a tile held 2 - 3 times the records of an eta bin and the warp that owns them kept the other 19 waiting
+        // (38 % of its time in the bin walk against 1 - 30 %).  eta gets the remaining threads, as before.
+        double nbm_f = nbm, dm = dm_max, nbe = nbe_min, de = de_max;
+        if (ok) {
+            if (a.H_mu > 0) {
+                const double rmu = fmin(kPgDmaxMu, range);
+                nbm_f = fmin(ceil(2.0 * rmu / dm_max) + 1.0, (double)kPgMaxBins - nbe_min);
+                nbm_f = fmax(nbm_f, ceil(rmu / dm_max) + 1.0);
+                if (nbm_f + nbe_min <= (double)kPgMaxBins) dm = rmu / (nbm_f - 1.0);
+                else { nbm_f = nbm; dm = dm_max; }                                   // (cannot happen: ok guarantees nbm + nbe_min fits)
+            }
+            nbe = (double)kPgMaxBins - nbm_f;
+            de = range / (nbe - 1.0);
+        }
         hdr[0] = 1.0 / de; hdr[1] = de; hdr[2] = nbe;
-        hdr[3] = 1.0 / dm_max; hdr[4] = dm_max; hdr[5] = nbm;
+        hdr[3] = 1.0 / dm; hdr[4] = dm; hdr[5] = nbm_f;
         hdr[6] = ok ? 1.0 : 0.0; hdr[7] = range;
     }
 }
+
+#ifdef FF_PG_TIMING
+__device__ unsigned long long g_pg_cyc[20][8];
+__device__ unsigned long long g_pg_maxbin[4];
+#define PGT(seg) do { if (lane == 0) { const long long t_ = clock64(); atomicAdd(&g_pg_cyc[warp][seg], (unsigned long long)(t_ - tprev)); tprev = t_; } } while (0)
+#else
+#define PGT(seg) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kPgMaxBins, 1) pgrad_binned_kernel(const PGradBinArgs a) {
     extern __shared__ __align__(16) double smem[];
@@ -182,6 +205,9 @@ __global__ void __launch_bounds__(kPgMaxBins, 1) pgrad_binned_kernel(const PGrad
     // measured 1.8x slower: every warp then runs the longest loop with most lanes idle).
     const int my_bin = tid;
 
+#ifdef FF_PG_TIMING
+    long long tprev = clock64();
+#endif
     const long long nrec = a.B * NS;
     // stage-input / adjoint rows of one tile, asynchronously (cp.async) into buffer `buf`
     auto fetch_tile = [&](long long r0, int buf) {
@@ -209,8 +235,10 @@ __global__ void __launch_bounds__(kPgMaxBins, 1) pgrad_binned_kernel(const PGrad
         const int nr = (int)min((long long)R, nrec - r0);
         const double* ysk = ysk0 + (size_t)buf * R * 2 * D;
         const double* kdl = kdl0 + buf * ((R + 1) & ~1);
+        PGT(0);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                                      // this tile has landed; the previous one is consumed
+        PGT(1);
         int* ovf_count = ovf_counts + buf;
         if (tid == 0) ovf_counts[buf ^ 1] = 0;                // for the next tile (last read before the barrier above)
         // ---- records: d, weights, bin --------------------------------------------------------
@@ -247,7 +275,9 @@ __global__ void __launch_bounds__(kPgMaxBins, 1) pgrad_binned_kernel(const PGrad
                 ovf[atomicAdd(ovf_count, 1)] = (unsigned short)g;
             }
         }
+        PGT(2);
         __syncthreads();
+        PGT(3);
         fetch_tile(r0 + (long long)gridDim.x * R, buf ^ 1);   // overlaps the scan, scatter and bin walk below
         // ---- exclusive scan of the bin counts ---------------------------------------------------
         {
@@ -272,6 +302,15 @@ __global__ void __launch_bounds__(kPgMaxBins, 1) pgrad_binned_kernel(const PGrad
             if (bin != 0xFFFF) sorted[off[bin] + atomicAdd(&cur[bin], 1)] = (unsigned short)g;
         }
         __syncthreads();
+        PGT(4);
+#ifdef FF_PG_TIMING
+        {   // statistics outside the timed segments: per warp the largest bin of this tile
+            unsigned long long c = my_bin < nbins ? cnt[my_bin] : 0;
+            for (int o = 16; o > 0; o >>= 1) { unsigned long long v = __shfl_xor_sync(0xffffffffu, c, o); c = v > c ? v : c; }
+            if (lane == 0) { atomicAdd(&g_pg_maxbin[3], c); atomicMax(&g_pg_maxbin[0], c); if (warp == 0) atomicAdd(&g_pg_maxbin[2], 1ull); }
+            tprev = clock64();
+        }
+#endif
         // ---- every thread walks the records of ITS bin, two records in lock-step (the power chain is serial) ---
         if (my_bin < nbins) {
             const int p0 = off[my_bin], p1 = p0 + cnt[my_bin];
@@ -297,6 +336,7 @@ __global__ void __launch_bounds__(kPgMaxBins, 1) pgrad_binned_kernel(const PGrad
                 for (int m = 0; m < kPgMom; ++m) { MA[m] = fma(A, pw, MA[m]); MB[m] = fma(Bc, pw, MB[m]); pw *= t; }
             }
         }
+        PGT(5);
         // ---- records outside the node range: direct sums, one hidden unit per thread ----------------
         const int novf = *ovf_count;
         if (novf > 0 && dir_on) {
