@@ -356,6 +356,10 @@ def run_config(args):
     steps, warmup = max(args.steps, 20), max(args.warmup, 5)
     for _ in range(warmup):
         step()
+    # the cost of an iteration depends on the state of the optimisation (node ranges of the binned gradient, records
+    # beyond them): both timed loops start from this snapshot and see the same sequence of iterations
+    import copy
+    snap = (copy.deepcopy(model.state_dict()), copy.deepcopy(opt.state_dict()))
     eloc_events.clear()
     launches0 = L.lib().ff_launch_count()
     sampler.start()
@@ -368,6 +372,7 @@ def run_config(args):
     ms = t0.elapsed_time(t1)
     launches = L.lib().ff_launch_count() - launches0
     eloc_ms = sum(a.elapsed_time(b) for a, b in eloc_events) / max(len(eloc_events), 1)
+    model.load_state_dict(snap[0]); opt.load_state_dict(snap[1])
     host_params = torch.cat([p.detach().reshape(-1) for p in params]).cpu().pin_memory()
     host_out = torch.empty(nparam + 5, dtype=torch.float64).pin_memory()
     dev_params = torch.empty(nparam, device=dev)
