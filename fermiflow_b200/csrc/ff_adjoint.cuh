@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
                 } else {
                     rx = y[2 * it_i]; ry = y[2 * it_i + 1]; kx = k[2 * it_i]; ky = k[2 * it_i + 1];
                 }
-                const double d = sqrt(fma(rx, rx, ry * ry));
+                const double d2 = fma(rx, rx, ry * ry);
+                const double inv_d = rsqrt(d2), d = d2 * inv_d;       // one reciprocal square root instead of sqrt and a division
                 if (RECOMPUTE) {
                     double f[4];
                     if (!radial_table_eval<2>(my_rt, d, f)) {
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
                 }
                 const double alpha = fma(kx, rx, ky * ry);
                 const double q1 = (it_pair ? 2.0 : 1.0) * fma(f2, d, 3.0 * f1);
-                const double c = (alpha * f1 - kd * q1) / d;
+                const double c = (alpha * f1 - kd * q1) * inv_d;
                 vec(it_w)[2 * it_p] = fma(kx, f0, c * rx);
                 vec(it_w)[2 * it_p + 1] = fma(ky, f0, c * ry);
             }
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
 // ---------------------------------------------------------------------------------------
 __host__ __device__ inline int adjoint_warp_slice(int D, int P) { return 6 * D + 2 * P; }
 
-template <bool RECOMPUTE>
+template <bool RECOMPUTE, bool PREFETCH = true>
 __global__ void __launch_bounds__(256, 4) adjoint_warp_kernel(const AdjArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
@@ -207,6 +208,17 @@ __global__ void __launch_bounds__(256, 4) adjoint_warp_kernel(const AdjArgs a) {
         __syncwarp();
         for (int stage = NS - 1; stage >= 0; --stage) {
             const int sub = stage & 3;
+            // the stash of the stage after this one (5 KB, contiguous) is pulled into L2 by the bulk-copy engine while
+            // this stage computes: no registers, no shared memory; the sweep is latency bound on exactly these loads
+            if (PREFETCH && lane == 0 && stage > 0) {
+                // (16-byte granularity: the start is rounded down, the end too; both stay inside the stash)
+                auto bulk_prefetch = [](const double* p, int bytes) {
+                    const unsigned long long a0 = reinterpret_cast<unsigned long long>(p), a1 = (a0 + bytes) & ~15ull, as = a0 & ~15ull;
+                    if (a1 > as) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(as), "r"((unsigned)(a1 - as)) : "memory");
+                };
+                bulk_prefetch(a.stash_y + (b * NS + stage - 1) * D, D * 8);
+                if (!RECOMPUTE) bulk_prefetch(a.stash_c + ((b * NS + stage - 1) * P) * 3, P * 24);
+            }
             for (int e = lane; e < D; e += 32) {                         // stage adjoint kbar, stage input y
                 const double u = ubar[e];
                 double k;
@@ -236,7 +248,8 @@ __global__ void __launch_bounds__(256, 4) adjoint_warp_kernel(const AdjArgs a) {
                     const int i = p - NP;
                     rx = yy[2 * i]; ry = yy[2 * i + 1]; kx = kb[2 * i]; ky = kb[2 * i + 1];
                 }
-                const double d = sqrt(fma(rx, rx, ry * ry));
+                const double d2 = fma(rx, rx, ry * ry);
+                const double inv_d = rsqrt(d2), d = d2 * inv_d;       // one reciprocal square root instead of sqrt and a division
                 if (RECOMPUTE) {
                     double f[4];
                     if (!radial_table_eval<2>(is_pair ? rt_e : rt_m, d, f)) {
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(256, 4) adjoint_warp_kernel(const AdjArgs a) {
                 }
                 const double alpha = fma(kx, rx, ky * ry);
                 const double q1 = (is_pair ? 2.0 : 1.0) * fma(f2, d, 3.0 * f1);
-                const double c = (alpha * f1 - kd * q1) / d;
+                const double c = (alpha * f1 - kd * q1) * inv_d;
                 vec[2 * p] = fma(kx, f0, c * rx);
                 vec[2 * p + 1] = fma(ky, f0, c * ry);
             }
