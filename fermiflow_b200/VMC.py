@@ -26,11 +26,25 @@ from .utils import eloc_sweep
 
 
 def _potential_flags(pair_potential, sp_potential):
-    if not isinstance(pair_potential, CoulombPairPotential):
-        raise NotImplementedError("the CUDA path implements the reference's CoulombPairPotential only")
-    if sp_potential is not None and not isinstance(sp_potential, HO):
-        raise NotImplementedError("the CUDA path implements the reference's HO single-particle potential only")
-    return float(pair_potential.Z), sp_potential is not None
+    """(Z, harmonic) for the fused sweep: the reference's CoulombPairPotential and HO are evaluated inside it
+    (VMC.py:27-28 accepts any object with V(x); others are added by _add_external_potentials)."""
+    Z = float(pair_potential.Z) if type(pair_potential) is CoulombPairPotential else 0.0
+    return Z, type(sp_potential) is HO
+
+
+def _add_external_potentials(owner, res, x):
+    """Potentials the fused sweep does not know (any object with V(x) other than CoulombPairPotential / HO,
+    VMC.py:52-55): evaluated by their own V on the device and added to the potential and the local energy."""
+    extra = None
+    if type(owner.pair_potential) is not CoulombPairPotential:
+        extra = owner.pair_potential.V(x.detach())
+    if owner.sp_potential is not None and type(owner.sp_potential) is not HO:
+        v = owner.sp_potential.V(x.detach())
+        extra = v if extra is None else extra + v
+    if extra is not None:
+        res.potential = res.potential + extra
+        res.eloc = res.eloc + extra
+    return res
 
 
 class _LogpFromSweep(torch.autograd.Function):
@@ -158,7 +172,8 @@ class GSVMC(_VMCBase):
 
     def local_energy(self, x, stash=False):
         """log p, grad, laplacian, kinetic, potential, E_loc at x (VMC.py:44-55)."""
-        return eloc_sweep(self.cnf, x, self._orb(x.device), None, self.nup, self._Z, self._harmonic, stash=stash)
+        res = eloc_sweep(self.cnf, x, self._orb(x.device), None, self.nup, self._Z, self._harmonic, stash=stash)
+        return _add_external_potentials(self, res, x)
 
     def forward(self, batch):                                         # VMC.py:41-61
         _, x = self.sample((batch,))
@@ -271,7 +286,7 @@ class BetaVMC(_VMCBase):
     def forward(self, batch):                                          # VMC.py:120-171
         _, x = self.sample((batch,))
         table, state = self._state_table(x.device), self.state_indices
-        res = eloc_sweep(self.cnf, x, table, state, self.nup, self._Z, self._harmonic, stash=True)
+        res = _add_external_potentials(self, eloc_sweep(self.cnf, x, table, state, self.nup, self._Z, self._harmonic, stash=True), x)
         self.last = res.without_stash()
         Eloc = res.eloc
         obs, nglobal, gradF_phi, Eloc_x_mean = _beta_estimators(Eloc, state.long(), self.log_state_weights, self.beta,

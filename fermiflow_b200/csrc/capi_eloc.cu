@@ -152,9 +152,9 @@ int launch_eloc5(ff::FlowArgs& a, cudaStream_t st) {
 // Statically specialised E_loc sweeps (ff_eloc4.cuh; ff_eloc2.cuh under option "eloc_v2" or without the Taylor tables) for the particle numbers of the BASELINE.json configs; anything
 // else, or "eloc_generic", runs the generic flow_kernel<MODE_ELOC>.
 int try_eloc_static(ff::FlowArgs& a, cudaStream_t st) {
-    if (opt(OPT_ELOC_GENERIC) || a.H_mu <= 0) return FF_FALLBACK;
+    if (opt(OPT_ELOC_GENERIC)) return FF_FALLBACK;
     if (!opt(OPT_ELOC_V2) && a.rt_eta != nullptr) {
-        if (opt(OPT_ELOC_V4)) {
+        if (opt(OPT_ELOC_V4) && a.H_mu > 0) {
             switch (a.n) {
                 case 20: return launch_eloc4<20, 1>(a, st);
                 case 12: return launch_eloc4<12, 1>(a, st);
@@ -162,13 +162,23 @@ int try_eloc_static(ff::FlowArgs& a, cudaStream_t st) {
                 default: break;
             }
         }
-        switch (a.n) {
-            case 20: return launch_eloc5<20, 1>(a, st);
-            case 12: return launch_eloc5<12, 1>(a, st);
-            case 6: return launch_eloc5<6, 1>(a, st);
-            default: break;
+        if (a.H_mu > 0) {
+            switch (a.n) {
+                case 20: return launch_eloc5<20, 1>(a, st);
+                case 12: return launch_eloc5<12, 1>(a, st);
+                case 6: return launch_eloc5<6, 1>(a, st);
+                default: break;
+            }
+        } else {                 // reference drivers' --nomu: no one-body backflow
+            switch (a.n) {
+                case 20: return launch_eloc5<20, 0>(a, st);
+                case 12: return launch_eloc5<12, 0>(a, st);
+                case 6: return launch_eloc5<6, 0>(a, st);
+                default: break;
+            }
         }
     }
+    if (a.H_mu <= 0) return FF_FALLBACK;
     switch (a.n) {
         case 20: return launch_eloc2<20, 1>(a, st);
         case 12: return launch_eloc2<12, 1>(a, st);

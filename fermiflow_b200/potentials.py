@@ -13,7 +13,9 @@ def _potential(x, Z, harmonic):
 
 
 class SPPotential(object):
-    pass
+    """Single-particle potential: subclasses give V(x) -> (batch,) (potentials.py:5-14).  `HO` is evaluated inside
+    the fused E_loc sweep; any other subclass is evaluated through its own V (torch ops on the device) and added
+    to the sweep's kinetic energy."""
 
 
 class HO(SPPotential):
@@ -22,7 +24,17 @@ class HO(SPPotential):
 
 
 class PairPotential(object):
-    pass
+    """Pair potential V = sum_{i<j} v(|r_i - r_j|) (potentials.py:18-39): subclasses give v(rij).
+    `CoulombPairPotential` is evaluated inside the fused E_loc sweep; any other subclass goes through rij / V below
+    (torch ops on the device) and is added to the sweep's kinetic energy."""
+
+    def rij(self, x):                               # potentials.py:23-31
+        n = x.shape[-2]
+        row, col = torch.triu_indices(n, n, offset=1, device=x.device)
+        return (x[:, row] - x[:, col]).norm(dim=-1)
+
+    def V(self, x):                                 # potentials.py:33-39
+        return self.v(self.rij(x)).sum(dim=-1)
 
 
 class CoulombPairPotential(PairPotential):

@@ -140,6 +140,45 @@ def test_potentials_vs_reference(dev, golden):
     close(CoulombPairPotential(float(g["Z"])).V(x), g["coulomb"], 1e-13)
 
 
+def test_user_defined_potentials(dev, O):
+    """VMC.py:27-28 accepts any potential object: a PairPotential subclass that only defines v(rij) (here a Yukawa
+    interaction) and a single-particle potential with its own V (a quartic trap) are evaluated by their torch code and
+    added to the kinetic energy of the fused sweep; log p, gradient and Laplacian are those of the Coulomb run."""
+    from fermiflow_b200 import Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
+    from fermiflow_b200.potentials import PairPotential, SPPotential
+
+    class Yukawa(PairPotential):
+        def v(self, rij):
+            return 1.7 * torch.exp(-0.6 * rij) / rij
+
+    class Quartic(SPPotential):
+        def V(self, x):
+            return 0.25 * (x ** 4).sum(dim=(-2, -1))
+
+    eta, mu = rand_mlp(8, 3, 0.05, dev), rand_mlp(6, 4, 0.05, dev)
+    cnf = CNF(Backflow(eta, mu=mu), (0.0, 1.0), nsteps=8)
+    ref_model = GSVMC(3, 2, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(2.0), sp_potential=HO()).to(dev)
+    model = GSVMC(3, 2, HO2D(), FreeFermion(dev), cnf, Yukawa(), sp_potential=Quartic()).to(dev)
+    torch.manual_seed(3)
+    x = 0.9 * torch.randn(7, 5, 2, device=dev)
+    r0, r = ref_model.local_energy(x), model.local_energy(x)
+    for k in ("logp", "grad", "lap", "kinetic"):
+        assert torch.equal(getattr(r, k), getattr(r0, k))
+    xc = x.cpu()
+    iu = torch.triu_indices(5, 5, offset=1)
+    rij = (xc[:, iu[0]] - xc[:, iu[1]]).norm(dim=-1)
+    pot = (1.7 * torch.exp(-0.6 * rij) / rij).sum(-1) + 0.25 * (xc ** 4).sum(dim=(-2, -1))
+    close(r.potential, pot, 1e-13)
+    close(r.eloc, r0.kinetic.cpu() + pot, 1e-12)
+    # the whole iteration runs with them (energy gradient through the flow)
+    g = model(64)
+    g.backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters())
+    # Coulomb + no single-particle potential (sp_potential=None, VMC.py:22-28)
+    bare = GSVMC(3, 2, HO2D(), FreeFermion(dev), cnf, CoulombPairPotential(2.0)).to(dev)
+    close(bare.local_energy(x).potential, CoulombPairPotential(2.0).V(x))
+
+
 def _golden_model(g, dev, nsteps):
     from fermiflow_b200 import Backflow, CNF, HO2D, FreeFermion, GSVMC, HO, CoulombPairPotential
     eta, mu = mlp_from(g, "eta", dev), mlp_from(g, "mu", dev)
@@ -187,7 +226,9 @@ CASES = [  # nup, ndown, H_eta, H_mu, nsteps, batch
     (6, 6, 16, 16, 8, 9),
     (12, 0, 10, 10, 4, 6),      # spin-polarised N = 12 (BASELINE config 3): finale scratch extends into J1
     (5, 2, 50, 50, 4, 4),
-    (10, 10, 50, 50, 16, 3),    # the benchmark configuration (BASELINE configs[2]): eloc2_kernel<20,1>, warp adjoint, binned gradient
+    (10, 10, 50, 50, 16, 3),    # the benchmark configuration (BASELINE configs[2]): eloc5_kernel<20,1>, warp finale, warp adjoint, binned gradient
+    (3, 3, 12, 0, 8, 6),        # --nomu on the register-resident sweep (eloc5_kernel<6,0>)
+    (6, 6, 10, 0, 4, 4),        # ... eloc5_kernel<12,0>
 ]
 
 
