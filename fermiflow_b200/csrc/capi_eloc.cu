@@ -74,6 +74,7 @@ int launch_finale(const ff::FlowArgs& a, const double* fin, int stride, cudaStre
         switch ((2 * a.n + 7) / 8) {
             case 2: r = launch_finale_warp<2>(a, fin, stride, st); break;
             case 3: r = launch_finale_warp<3>(a, fin, stride, st); break;
+            case 4: r = launch_finale_warp<4>(a, fin, stride, st); break;
             case 5: r = launch_finale_warp<5>(a, fin, stride, st); break;
             default: break;
         }
@@ -121,12 +122,14 @@ int launch_eloc_reg(Kernel kernel, int threads, size_t smem, int fin_stride, ff:
     FF_CUDA(cudaMallocAsync((void**)&fin, (size_t)a.B * fin_stride * sizeof(double), st));
     struct Release { double* p; cudaStream_t s; ~Release() { cudaFreeAsync(p, s); } } release{fin, st};
     FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // two walkers per SM; what is left of the 256 KB stays L1 (the Taylor tables of the radial functions live there)
-    const int carve = (int)std::min<long long>(100, (2 * ((long long)smem + di.smem_reserved) * 100 + di.smem_sm - 1) / di.smem_sm);
-    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    // as many walkers per SM as registers and shared memory allow (two at N = 20, more for smaller blocks); what is left of
+    // the 256 KB stays L1 (the tails of the Taylor tables of the radial functions live there)
+    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     int occ = 0;
     FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
     if (occ < 1) return FF_FALLBACK;
+    const int carve = (int)std::min<long long>(100, ((long long)occ * ((long long)smem + di.smem_reserved) * 100 + di.smem_sm - 1) / di.smem_sm);
+    FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     const long long grid = std::min<long long>(a.B, (long long)di.sms * occ);
     kernel<<<(unsigned)grid, threads, smem, st>>>(a, fin);
     FF_LAUNCHED();
@@ -145,7 +148,8 @@ int launch_eloc5(ff::FlowArgs& a, cudaStream_t st) {
     const DevInfo di = dev_info();
     const long long half = std::min<long long>(di.smem_sm / 2 - di.smem_reserved, di.smem_optin);
     const long long room = half - (long long)g.total * 8;
-    a.rt_cache_nodes = (a.rt_eta != nullptr && room > 0 && !opt(OPT_NO_RT_CACHE)) ? (int)std::min<long long>(room / (8 * ff::kRtPitch), 1024) : 0;
+    // (at most 256 rows: small walker blocks leave the shared memory to more resident CTAs instead)
+    a.rt_cache_nodes = (a.rt_eta != nullptr && room > 0 && !opt(OPT_NO_RT_CACHE)) ? (int)std::min<long long>(room / (8 * ff::kRtPitch), 256) : 0;
     return launch_eloc_reg(ff::eloc5_kernel<SN, SMU>, g.threads, (size_t)(g.total + a.rt_cache_nodes * ff::kRtPitch) * 8, g.fin_stride, a, st);
 }
 
@@ -163,9 +167,21 @@ int try_eloc_static(ff::FlowArgs& a, cudaStream_t st) {
             }
         }
         if (a.H_mu > 0) {
-            switch (a.n) {
+            switch (a.n) {       // one walker per CTA; below 6 particles the generic sweep packs several walkers into a CTA
                 case 20: return launch_eloc5<20, 1>(a, st);
+                case 19: return launch_eloc5<19, 1>(a, st);
+                case 18: return launch_eloc5<18, 1>(a, st);
+                case 17: return launch_eloc5<17, 1>(a, st);
+                case 16: return launch_eloc5<16, 1>(a, st);
+                case 15: return launch_eloc5<15, 1>(a, st);
+                case 14: return launch_eloc5<14, 1>(a, st);
+                case 13: return launch_eloc5<13, 1>(a, st);
                 case 12: return launch_eloc5<12, 1>(a, st);
+                case 11: return launch_eloc5<11, 1>(a, st);
+                case 10: return launch_eloc5<10, 1>(a, st);
+                case 9: return launch_eloc5<9, 1>(a, st);
+                case 8: return launch_eloc5<8, 1>(a, st);
+                case 7: return launch_eloc5<7, 1>(a, st);
                 case 6: return launch_eloc5<6, 1>(a, st);
                 default: break;
             }

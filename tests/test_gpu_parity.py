@@ -229,6 +229,9 @@ CASES = [  # nup, ndown, H_eta, H_mu, nsteps, batch
     (10, 10, 50, 50, 16, 3),    # the benchmark configuration (BASELINE configs[2]): eloc5_kernel<20,1>, warp finale, warp adjoint, binned gradient
     (3, 3, 12, 0, 8, 6),        # --nomu on the register-resident sweep (eloc5_kernel<6,0>)
     (6, 6, 10, 0, 4, 4),        # ... eloc5_kernel<12,0>
+    (5, 5, 8, 8, 4, 3),         # register-resident sweep at the other particle numbers from 10 on: N = 10 (D8 = 24: padded blocks)
+    (7, 6, 10, 10, 4, 3),       # N = 13 (D = 26 in four row blocks)
+    (9, 8, 8, 8, 2, 2),         # N = 17 (D = 34 in five row blocks)
 ]
 
 
