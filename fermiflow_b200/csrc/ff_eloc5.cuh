@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
     __syncthreads();
 
     // Owners and workers run their own stage loops (the register allocation is the larger of the two, not their sum);
-    // the CTA barriers inside are barrier 0 with all NT threads on both sides.
+    // the CTA-wide barriers inside are named barrier 4 with all NT threads, reached from both loops (barrier 0 is left to
+    // __syncthreads, which every thread has to execute at the same place).
     if (owner0) {
         for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
             // ---- initial state: K = 1 (registers and shared copy), gDelta = 0; y = x -------------------------------
@@ -207,8 +208,8 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                 S[G_.oL0 + e] = 0.0; S[G_.oL1 + e] = 0.0; S[G_.oLB + e] = 0.0; S[G_.oLC + e] = 0.0; S[G_.oYB + e] = 0.0; S[G_.oYC + e] = 0.0;
             }
             if (tid0 < 8) S[G_.oScal + tid0] = 0.0;
-            named_bar_sync(0, NT);
-            named_bar_sync(0, NT);                       // (the workers evaluate the radial functions of stage 0)
+            named_bar_sync(4, NT);
+            named_bar_sync(4, NT);                       // (the workers evaluate the radial functions of stage 0)
 #ifdef FF_E5_TIMING
             const int obs = (tid0 >> 5) == 0 ? 0 : (tid0 >> 5) == 1 ? 1 : -1;
             long long tprev = clock64();
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                 // ======== phase 1: M = K^T K of this stage ==========================================================
                 if (warp >= G_.G0 && warp < G_.G0 + G_.GWN) phase_gram5<SN, SMU>(S + G_.oM, Ks, warp - G_.G0, tid & 31);
                 E5T(0);
-                named_bar_sync(0, NT);
+                named_bar_sync(4, NT);
                 E5T(1);
                 // ======== phase 2 ===================================================================================
                 // ---- per-particle sums of this stage: k_y (y advances here), u, rho, diagonal of A -----------------
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                 }
                 gd = rk_elem(sub, gd, -h * ku, gdB, gdC);
                 E5T(5);
-                named_bar_sync(0, NT);
+                named_bar_sync(4, NT);
                 E5T(7);
             }
             // ---- final state to global memory: gDelta, J = K^T row-major (the workers write the vectors) -----------
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                         }
                 }
             }
-            named_bar_sync(0, NT);
+            named_bar_sync(4, NT);
         }
     } else {
         // item of this worker lane (one item per lane: P <= NWRK)
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
         for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
             // the item of the coming stage: r, d, 1/d and the radial function with three derivatives
             double rx = 0.0, ry = 0.0, dd = 1.0, inv_d = 1.0, f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
-            named_bar_sync(0, NT);                       // (the owners have set the initial state)
+            named_bar_sync(4, NT);                       // (the owners have set the initial state)
 #ifdef FF_E5_TIMING
             const int obs = (tid0 >> 5) == OW ? 2 : (tid0 >> 5) == OW + WW - 1 ? 3 : -1;
             long long tprev = clock64();
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                         }
                     }
                     E5T(0);
-                    named_bar_sync(0, NT);
+                    named_bar_sync(4, NT);
                     E5T(1);
                     // ======== phase 2 ===============================================================================
                     // ---- contraction of this lane's item with M = J J^T --------------------------------------------
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                     f0 = f[0]; f1 = f[1]; f2 = f[2]; f3 = f[3];
                 }
                 E5T(6);
-                named_bar_sync(0, NT);
+                named_bar_sync(4, NT);
                 E5T(7);
             }
             // ---- final state to global memory: y, L, (Delta, lapDelta) ----------------------------------------------
@@ -526,7 +527,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                     if (a.delta_out) a.delta_out[b] = S[G_.oScal];
                 }
             }
-            named_bar_sync(0, NT);
+            named_bar_sync(4, NT);
         }
     }
 }
