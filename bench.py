@@ -540,7 +540,7 @@ def cpu_baseline(args, budget_s):
 
 def run_reference(args):
     """--impl reference: the reference's CPU path on the host cores, K timed steps of `--ref-walkers` walkers (reduced
-    only if K steps would not fit ~4 minutes), plus one step at a quarter of that batch as a second data point."""
+    until K steps fit ~8 minutes), plus single steps at other batch sizes as further data points."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
@@ -549,16 +549,26 @@ def run_reference(args):
     n = args.nup + args.ndown
     for _ in range(max(1, min(args.warmup, 1))):
         R.time_vmc_iteration(args.nup, args.ndown, args.hidden, args.Z, 1, seed=1, equil=2)
+    # K timed steps must fit a few minutes: their batch is the largest power-of-two fraction of --ref-walkers for which
+    # K steps take at most ~8 minutes (the cost of a step grows ~ batch^0.6 in this range); ONE extra step at --ref-walkers is
+    # timed beside them so that the saturation of the CPU throughput with the batch is on record (the reference's default
+    # batch is 8000, FermionHO2D.py:30; 32 walkers of N = 20 take ~46 s on 16 threads)
+    t_start = time.time()
     small = max(2, args.ref_walkers // 4)
     t_small = R.time_vmc_iteration(args.nup, args.ndown, args.hidden, args.Z, small, seed=5)
     walkers = args.ref_walkers
-    while walkers > small and args.steps * t_small * (walkers / small) ** 0.6 > 240.0:
+    while walkers > max(2, small // 2) and args.steps * t_small * (walkers / small) ** 0.6 > 480.0:
         walkers //= 2
     ts = [R.time_vmc_iteration(args.nup, args.ndown, args.hidden, args.Z, walkers, seed=10 + i) for i in range(args.steps)]
     tot = sum(ts)
     value = walkers * args.steps / tot
-    pts = [{"walkers": small, "value": small / t_small, "seconds": round(t_small, 1)},
-           {"walkers": walkers, "value": value, "seconds": round(tot / args.steps, 1)}]
+    pts = [{"walkers": small, "value": small / t_small, "seconds": round(t_small, 1)}]
+    if walkers != small:
+        pts.append({"walkers": walkers, "value": value, "seconds": round(tot / args.steps, 1)})
+    if walkers < args.ref_walkers and time.time() - t_start < 600.0:
+        t_big = R.time_vmc_iteration(args.nup, args.ndown, args.hidden, args.Z, args.ref_walkers, seed=99)
+        pts.append({"walkers": args.ref_walkers, "value": args.ref_walkers / t_big, "seconds": round(t_big, 1)})
+    pts.sort(key=lambda q: q["walkers"])
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
@@ -568,7 +578,7 @@ def run_reference(args):
                    "ref_walkers": walkers, "cores": torch.get_num_threads()},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "ref_walkers": walkers, "batch_points": pts,
-                         "sample": "%d VMC iterations of %d walkers (and one of %d) of the %s" % (args.steps, walkers, small, _ref_note(n))},
+                         "sample": "%d VMC iterations of %d walkers (batch_points: single iterations at other batch sizes) of the %s" % (args.steps, walkers, _ref_note(n))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
