@@ -28,6 +28,9 @@ from .utils import eloc_sweep
 def _potential_flags(pair_potential, sp_potential):
     """(Z, harmonic) for the fused sweep: the reference's CoulombPairPotential and HO are evaluated inside it
     (VMC.py:27-28 accepts any object with V(x); others are added by _add_external_potentials)."""
+    for name, pot in (("pair_potential", pair_potential), ("sp_potential", sp_potential)):
+        if not (pot is None and name == "sp_potential") and not callable(getattr(pot, "V", None)):
+            raise TypeError("%s must provide V(x) (reference VMC.py:52-55), got %r" % (name, type(pot).__name__))
     Z = float(pair_potential.Z) if type(pair_potential) is CoulombPairPotential else 0.0
     return Z, type(sp_potential) is HO
 

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256, FF_WARP_MINB) flow_warp_kernel(const Flow
                     const int pp = ok[k] ? p : 0;
                     const int i = pair_i[pp], j = pair_j[pp];
                     rx[k] = Y[2 * i] - Y[2 * j]; ry[k] = Y[2 * i + 1] - Y[2 * j + 1];
-                    d[k] = sqrt(fma(rx[k], rx[k], ry[k] * ry[k]));
+                    { const double d2 = fma(rx[k], rx[k], ry[k] * ry[k]); d[k] = d2 * rsqrt(d2); }       // (cheaper than the IEEE sqrt; d = 0 has measure zero)
                 }
                 {
                     bool hit = true;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256, FF_WARP_MINB) flow_warp_kernel(const Flow
                     const bool ok = i0 < n;
                     const int i = ok ? i0 : 0;
                     rx[0] = Y[2 * i]; ry[0] = Y[2 * i + 1];
-                    d[0] = sqrt(fma(rx[0], rx[0], ry[0] * ry[0]));
+                    { const double d2 = fma(rx[0], rx[0], ry[0] * ry[0]); d[0] = d2 * rsqrt(d2); }
                     {
                         double g[4];
                         const bool hit = radial_table_eval<ORD>(rt_m, d[0], g) || !ok;

@@ -253,12 +253,12 @@ __global__ void __launch_bounds__(kPgMaxBins, 1) pgrad_binned_kernel(const PGrad
                 const int i = pair_i[p], j = pair_j[p];
                 rx = y[2 * i] - y[2 * j]; ry = y[2 * i + 1] - y[2 * j + 1];
                 kx = k[2 * i] - k[2 * j]; ky = k[2 * i + 1] - k[2 * j + 1];
-                d = sqrt(fma(rx, rx, ry * ry));
+                { const double d2 = fma(rx, rx, ry * ry); d = d2 * rsqrt(d2); }
                 A = fma(kx, rx, ky * ry) - 4.0 * kd; Bc = -2.0 * kd * d;
             } else {
                 const int i = p - NP;
                 rx = y[2 * i]; ry = y[2 * i + 1]; kx = k[2 * i]; ky = k[2 * i + 1];
-                d = sqrt(fma(rx, rx, ry * ry));
+                { const double d2 = fma(rx, rx, ry * ry); d = d2 * rsqrt(d2); }
                 A = fma(kx, rx, ky * ry) - 2.0 * kd; Bc = -kd * d;
             }
             const double kf = rint(d * (pr ? inv_de : inv_dm));

@@ -94,14 +94,23 @@ def test_mlp_mirror_matches_reference_mlp(golden):
         MLP(2, 3).kernel_params()
 
 
-def test_vmc_rejects_unsupported_potentials():
+def test_vmc_potential_objects():
+    """Any object with V(x) is a potential (reference VMC.py:27-28, 52-55); one without is refused at construction."""
     from fermiflow_b200 import MLP, Backflow, CNF, HO2D, FreeFermion, GSVMC
 
-    class Other:
+    class NoV:
         pass
+
+    class Quartic:
+        def V(self, x):
+            return (x ** 4).sum(dim=(-2, -1))
     cnf = CNF(Backflow(MLP(1, 4)), (0.0, 1.0))
-    with pytest.raises(NotImplementedError):
-        GSVMC(2, 0, HO2D(), FreeFermion("cpu"), cnf, Other())
+    with pytest.raises(TypeError):
+        GSVMC(2, 0, HO2D(), FreeFermion("cpu"), cnf, NoV())
+    with pytest.raises(TypeError):
+        GSVMC(2, 0, HO2D(), FreeFermion("cpu"), cnf, Quartic(), sp_potential=NoV())
+    model = GSVMC(2, 0, HO2D(), FreeFermion("cpu"), cnf, Quartic())
+    assert model._Z == 0.0 and not model._harmonic
 
 
 REFERENCE_CNF_KEYS = [   # list(CNF(Backflow(MLP(1, H), mu=MLP(1, H)), t_span).state_dict()) of reference src/flow.py:28,37
