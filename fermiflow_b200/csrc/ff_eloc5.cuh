@@ -149,6 +149,29 @@ __device__ __forceinline__ bool radial_eval_mirror(const RtHeader& T, const doub
     return true;
 }
 
+// FF_E5_RKACC: the RK combination of K enters K' = K A as the INITIAL VALUE of the tensor-core accumulators and the
+// workers store A already multiplied by the stage's step factor: the new K leaves the DMMA chain finished, with
+// 0 - 2 scalar FP64 instructions per element and stage instead of 2 - 5 (rk_elem).  With K_s the input of sub-stage s of
+// the 3/8 rule and A_s' = h c_s A_s, c = (1/3, 1, 1, 1/8):
+//   K_1 = K_0 + K_0 A_0'          K_2 = (2 K_0 - K_1) + K_1 A_1'          K_3 = (2 K_1 - K_2) + K_2 A_2'
+//   K_new = (6 K_2 - K_0) / 8 + 3/8 K_3 + K_3 A_3'
+// (same polynomial in h k_1 .. h k_4 as rk_elem).  Buffer KB holds K_0, then -K_0 / 8, then (6 K_2 - K_0) / 8; KC holds K_1.
+// FF_E5_ALMMA: (A L) on the tensor cores by the worker warps (A is symmetric: one more row operand against the same
+// B fragments as K A) instead of D lanes with D-term scalar chains.
+#ifndef FF_E5_RKACC
+#define FF_E5_RKACC 1
+#endif
+// FF_E5_ALITEM: (A L) from the items instead of from the assembled matrix: (A L)_i = sum_j A_ij (L_j - L_i) + (one-body
+// block) L_i, and the pair term changes sign with the orientation of the pair exactly like components 0, 1 of the
+// contraction records, so every item lane adds its 2-vector to those and the per-particle sums deliver k_L complete
+// (11 FP64 instructions per item lane instead of D-term chains on D lanes).
+#ifndef FF_E5_ALMMA
+#define FF_E5_ALMMA 0
+#endif
+#ifndef FF_E5_ALITEM
+#define FF_E5_ALITEM 1
+#endif
+
 #ifdef FF_E5_TIMING
 __device__ unsigned long long g_e5_cyc[4][16];
 #define E5T(seg) do { if (obs >= 0 && (tid0 & 31) == 0) { const long long t_ = clock64(); atomicAdd(&g_e5_cyc[obs][seg], (unsigned long long)(t_ - tprev)); tprev = t_; } } while (0)
@@ -272,8 +295,43 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                 E5T(3);
                 // ---- K' = K A on the tensor cores, k-step (rb, e): A operand = own registers -----------------------
                 double acc[NB][2];
+#if FF_E5_RKACC
+                {   // accumulators start from the RK combination of the earlier sub-stages (see FF_E5_RKACC above)
+                    double2* const PB = reinterpret_cast<double2*>(S + G_.oKB) + tid;
+                    double2* const PC = reinterpret_cast<double2*>(S + G_.oKC) + tid;
+#pragma unroll
+                    for (int rn = 0; rn < NB; ++rn) {
+                        const double k0 = Kr[rn][0], k1 = Kr[rn][1];
+                        if (sub == 0) {
+                            PB[rn * NOWN] = make_double2(k0, k1);
+                            acc[rn][0] = k0; acc[rn][1] = k1;
+                        } else if (sub == 1) {
+                            const double2 Bv = PB[rn * NOWN];
+                            acc[rn][0] = fma(2.0, Bv.x, -k0); acc[rn][1] = fma(2.0, Bv.y, -k1);
+                            PB[rn * NOWN] = make_double2(-0.125 * Bv.x, -0.125 * Bv.y);
+                            PC[rn * NOWN] = make_double2(k0, k1);
+                        } else if (sub == 2) {
+                            const double2 Bv = PB[rn * NOWN], Cv = PC[rn * NOWN];
+                            acc[rn][0] = fma(2.0, Cv.x, -k0); acc[rn][1] = fma(2.0, Cv.y, -k1);
+                            PB[rn * NOWN] = make_double2(fma(0.75, k0, Bv.x), fma(0.75, k1, Bv.y));
+                        } else {
+                            const double2 Bv = PB[rn * NOWN];
+                            acc[rn][0] = fma(0.375, k0, Bv.x); acc[rn][1] = fma(0.375, k1, Bv.y);
+                        }
+                    }
+                }
+                // ---- K u (for gDelta' = -u^T J): row sums over the quad, from the K at the stage input ------------------
+                double ku = 0.0;
+#pragma unroll
+                for (int rb = 0; rb < NB; ++rb) {
+                    const double2 uv = *reinterpret_cast<const double2*>(U + 8 * rb + 2 * t4);
+                    ku = fma(Kr[rb][0], uv.x, ku);
+                    ku = fma(Kr[rb][1], uv.y, ku);
+                }
+#else
 #pragma unroll
                 for (int rn = 0; rn < NB; ++rn) { acc[rn][0] = 0.0; acc[rn][1] = 0.0; }
+#endif
                 {
                     const double* Ab = A + t4 * DP + g8;
                     double bn[NB], bc[NB];
@@ -294,6 +352,16 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                     }
                 }
                 E5T(4);
+#if FF_E5_RKACC
+                // ---- the accumulators ARE the new K; shared copy for the Gram matrix of the next stage -----------------
+                ku += __shfl_xor_sync(0xffffffffu, ku, 1);
+                ku += __shfl_xor_sync(0xffffffffu, ku, 2);
+#pragma unroll
+                for (int rn = 0; rn < NB; ++rn) {
+                    Kr[rn][0] = acc[rn][0]; Kr[rn][1] = acc[rn][1];
+                    *reinterpret_cast<double2*>(Ks + (8 * warp + g8) * DP + 8 * rn + 2 * t4) = make_double2(Kr[rn][0], Kr[rn][1]);
+                }
+#else
                 // ---- K u (for gDelta' = -u^T J): row sums over the quad --------------------------------------------
                 double ku = 0.0;
 #pragma unroll
@@ -318,6 +386,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                     if (sub <= 2) PC[rn * NOWN] = Cv;
                     *reinterpret_cast<double2*>(Ks + (8 * warp + g8) * DP + 8 * rn + 2 * t4) = make_double2(Kr[rn][0], Kr[rn][1]);
                 }
+#endif
                 gd = rk_elem(sub, gd, -h * ku, gdB, gdC);
                 E5T(5);
                 named_bar_sync(4, NT);
@@ -355,6 +424,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
         for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
             // the item of the coming stage: r, d, 1/d and the radial function with three derivatives
             double rx = 0.0, ry = 0.0, dd = 1.0, inv_d = 1.0, f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
+            double sDl = 0.0, sDlB = 0.0, sDlC = 0.0, sLd = 0.0, sLdB = 0.0, sLdC = 0.0;     // shares of Delta, lapDelta (lanes wl < n)
             named_bar_sync(4, NT);                       // (the owners have set the initial state)
 #ifdef FF_E5_TIMING
             const int obs = (tid0 >> 5) == OW ? 2 : (tid0 >> 5) == OW + WW - 1 ? 3 : -1;
@@ -375,7 +445,6 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                 double* const R1 = S + G_.oR1;
                 double* const Y = S + G_.oY;
                 double* const U = S + G_.oU;
-                double* const scal = S + G_.oScal;
                 double* const Lc = S + ((stage & 1) ? G_.oL1 : G_.oL0);          // L at the stage input
                 double* const Ln = S + ((stage & 1) ? G_.oL0 : G_.oL1);
                 if (stage >= 0) {
@@ -395,7 +464,14 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                         const double q2 = mult * fma(f3, dd, 4.0 * f2);
                         ccq = q1 * inv_d;
                         ceq = (q2 - ccq) * inv_d2;
+#if FF_E5_RKACC
+                        // A is stored multiplied by the step factor h c_sub of this sub-stage (see FF_E5_RKACC)
+                        const double hs = sub == 0 ? h * (1.0 / 3.0) : sub == 3 ? h * 0.125 : h;
+                        const double caS = hs * ca, f0S = hs * f0;
+                        const double a00 = fma(caS * rx, rx, f0S), a01 = caS * rx * ry, a11 = fma(caS * ry, ry, f0S);
+#else
                         const double a00 = fma(ca * rx, rx, f0), a01 = ca * rx * ry, a11 = fma(ca * ry, ry, f0);
+#endif
                         const double v0 = f0 * rx, v1 = f0 * ry, v2 = ccq * rx, v3 = ccq * ry, v4 = fma(f1, dd, 2.0 * f0);
                         if (it_pair) {          // both orientations of the pair; off-diagonal blocks of A (row-permuted storage)
                             double* const Rij = R1 + it_i * RP + it_j;
@@ -443,8 +519,20 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                         const double wrx = fma(w00, rx, w01 * ry), wry = fma(w01, rx, w11 * ry);
                         const double trw = w00 + w11, rwr = fma(rx, wrx, ry * wry);
                         double* const G2 = S + G_.oG2 + 3 * it_p;
+#if FF_E5_ALITEM
+                        double dLx, dLy;
+                        {
+                            const double2 li = *reinterpret_cast<const double2*>(Lc + i2);
+                            dLx = li.x; dLy = li.y;
+                            if (it_pair) { const double2 lj = *reinterpret_cast<const double2*>(Lc + j2); dLx -= lj.x; dLy -= lj.y; }
+                        }
+                        const double tl = ca * fma(rx, dLx, ry * dLy);
+                        G2[0] = fma(ca, fma(2.0, wrx, trw * rx), cb_ * rwr * rx) + fma(f0, dLx, tl * rx);
+                        G2[1] = fma(ca, fma(2.0, wry, trw * ry), cb_ * rwr * ry) + fma(f0, dLy, tl * ry);
+#else
                         G2[0] = fma(ca, fma(2.0, wrx, trw * rx), cb_ * rwr * rx);
                         G2[1] = fma(ca, fma(2.0, wry, trw * ry), cb_ * rwr * ry);
+#endif
                         G2[2] = fma(ccq, trw, ceq * rwr);
                     }
                     E5T(2);
@@ -454,12 +542,63 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                         const int g2_i = wl / 3, g2_k = wl - 3 * g2_i;
                         if (g2_i < n) {
                             const double acc = gather3<SN, SMU>(S + G_.oG2, g2_i, g2_k);
+#if FF_E5_ALITEM
+                            // components 0, 1 are k_L = A L + (d2v : M) complete (see FF_E5_ALITEM): L advances here
+                            if (g2_k < 2) {
+                                const int m = 2 * g2_i + g2_k;
+                                Ln[m] = rk_elem(sub, Lc[m], h * acc, S[G_.oLB + m], S[G_.oLC + m]);
+                            } else S[G_.oP2 + g2_i] = acc;
+#else
                             if (g2_k < 2) S[G_.oKLx + 2 * g2_i + g2_k] = acc; else S[G_.oP2 + g2_i] = acc;
+#endif
                         }
                     }
                     E5T(3);
                     named_bar_sync(2, NT);                // the owners' sums of this stage are in place: y, A, u, rho
                     E5T(4);
+#if FF_E5_ALITEM
+                    // (L' = A L + (d2v : M) came out of the per-particle sums above)
+#elif FF_E5_ALMMA
+                    // ---- L' = A L + (d2v : M) on the tensor cores: A is symmetric, so (A L)^T = L^T A is one more row
+                    // operand against the B fragments of K A; worker warp w forms the column blocks w, w + WW, ... (all
+                    // eight rows of the product are the same: lanes g8 = 0 keep columns 2 t4, 2 t4 + 1)
+                    {
+                        const int lane = tid & 31, g8 = lane >> 2, t4 = lane & 3;
+#if FF_E5_RKACC
+                        const double inv_c = sub == 0 ? 3.0 : sub == 3 ? 8.0 : 1.0, hx = h;       // A holds h c_sub A
+#else
+                        const double inv_c = h, hx = h;
+#endif
+                        for (int rn = warp - OW; rn < NB; rn += WW) {
+                            const double* Ab = A + t4 * DP + g8 + 8 * rn;
+                            double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0};
+                            double bfr[2 * NB], lfr[2 * NB];
+#pragma unroll
+                            for (int ks = 0; ks < 2 * NB; ++ks) {
+                                bfr[ks] = Ab[(8 * (ks >> 1) + 4 * (ks & 1)) * DP];
+                                lfr[ks] = Lc[8 * (ks >> 1) + 2 * t4 + (ks & 1)];
+                            }
+#pragma unroll
+                            for (int ks = 0; ks < 2 * NB; ++ks) {
+                                if (ks & 1) dmma_ordered(a1[0], a1[1], lfr[ks], bfr[ks]);
+                                else dmma_ordered(a0[0], a0[1], lfr[ks], bfr[ks]);
+                            }
+                            if (g8 == 0) {
+                                const int m = 8 * rn + 2 * t4;
+                                const double2 kx = *reinterpret_cast<const double2*>(S + G_.oKLx + m);
+                                const double2 lc = *reinterpret_cast<const double2*>(Lc + m);
+                                double2 lb = *reinterpret_cast<const double2*>(S + G_.oLB + m);
+                                double2 lcc = *reinterpret_cast<const double2*>(S + G_.oLC + m);
+                                double2 ln;
+                                ln.x = rk_elem(sub, lc.x, fma(a0[0] + a1[0], inv_c, hx * kx.x), lb.x, lcc.x);
+                                ln.y = rk_elem(sub, lc.y, fma(a0[1] + a1[1], inv_c, hx * kx.y), lb.y, lcc.y);
+                                *reinterpret_cast<double2*>(Ln + m) = ln;
+                                *reinterpret_cast<double2*>(S + G_.oLB + m) = lb;
+                                *reinterpret_cast<double2*>(S + G_.oLC + m) = lcc;
+                            }
+                        }
+                    }
+#else
                     // ---- L' = A L + (d2v : M), lane m < D: column m of the symmetric A along the lanes -------------
                     if (wl < D) {
                         const double* Ac = A + wl;
@@ -470,24 +609,24 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                             if ((k & 3) == 0) s0 = fma(av, lv, s0); else if ((k & 3) == 1) s1 = fma(av, lv, s1);
                             else if ((k & 3) == 2) s2 = fma(av, lv, s2); else s3 = fma(av, lv, s3);
                         }
-                        const double kL = ((s0 + s1) + (s2 + s3)) + S[G_.oKLx + wl];
-                        Ln[wl] = rk_elem(sub, Lc[wl], h * kL, S[G_.oLB + wl], S[G_.oLC + wl]);
+#if FF_E5_RKACC
+                        const double inv_c = sub == 0 ? 3.0 : sub == 3 ? 8.0 : 1.0;
+                        const double hkL = fma((s0 + s1) + (s2 + s3), inv_c, h * S[G_.oKLx + wl]);
+#else
+                        const double hkL = h * (((s0 + s1) + (s2 + s3)) + S[G_.oKLx + wl]);
+#endif
+                        Ln[wl] = rk_elem(sub, Lc[wl], hkL, S[G_.oLB + wl], S[G_.oLC + wl]);
                     }
-                    if (warp == OW + WW - 1) {          // Delta' = -rho, lapDelta' = -(sum_i part2_i + u.L)
-                        const int lane = tid & 31;
-                        double ul = 0.0, rho = 0.0, lp = 0.0;
-                        for (int k = lane; k < D; k += 32) ul = fma(U[k], Lc[k], ul);
-                        if (lane < n) { rho = S[G_.oP1 + lane]; lp = S[G_.oP2 + lane]; }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            ul += __shfl_xor_sync(0xffffffffu, ul, o);
-                            rho += __shfl_xor_sync(0xffffffffu, rho, o);
-                            lp += __shfl_xor_sync(0xffffffffu, lp, o);
-                        }
-                        if (lane == 0) {
-                            scal[0] = rk_elem(sub, scal[0], -h * rho, scal[1], scal[2]);
-                            scal[3] = rk_elem(sub, scal[3], -h * (lp + ul), scal[4], scal[5]);
-                        }
+#endif
+                    // Delta' = -rho, lapDelta' = -(sum_i part2_i + u.L): the RK combination is linear, so lane i < n carries
+                    // the share of particle i through all stages in registers and the shares meet once, after the sweep
+                    // (a per-stage warp reduction was a 25-deep FP64 chain on the critical path of the workers)
+                    if (wl < n) {
+                        const double rho = S[G_.oP1 + wl];
+                        const double2 uv = *reinterpret_cast<const double2*>(U + 2 * wl), lv = *reinterpret_cast<const double2*>(Lc + 2 * wl);
+                        const double lp = fma(uv.x, lv.x, fma(uv.y, lv.y, S[G_.oP2 + wl]));
+                        sDl = rk_elem(sub, sDl, -h * rho, sDlB, sDlC);
+                        sLd = rk_elem(sub, sLd, -h * lp, sLdB, sLdC);
                     }
                     E5T(5);
                 }
@@ -522,9 +661,17 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                     F[e] = S[G_.oY + e]; F[D + e] = S[G_.oL0 + e];       // NS is even: L ends in buffer 0
                     if (a.y_out) a.y_out[b * D + e] = S[G_.oY + e];
                 }
-                if (wl == 0) {
-                    F[3 * D] = S[G_.oScal]; F[3 * D + 1] = S[G_.oScal + 3];
-                    if (a.delta_out) a.delta_out[b] = S[G_.oScal];
+                if ((tid0 >> 5) == OW) {          // the per-particle shares of Delta and lapDelta (n <= 32 lanes of this warp)
+                    double dl = wl < n ? sDl : 0.0, ld = wl < n ? sLd : 0.0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        dl += __shfl_xor_sync(0xffffffffu, dl, o);
+                        ld += __shfl_xor_sync(0xffffffffu, ld, o);
+                    }
+                    if (wl == 0) {
+                        F[3 * D] = dl; F[3 * D + 1] = ld;
+                        if (a.delta_out) a.delta_out[b] = dl;
+                    }
                 }
             }
             named_bar_sync(4, NT);
