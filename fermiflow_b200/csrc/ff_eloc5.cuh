@@ -140,12 +140,7 @@ __device__ __forceinline__ bool radial_eval_mirror(const RtHeader& T, const doub
 #pragma unroll
         for (int q = 0; q < kRtCoef / 2; ++q) { const double2 v = __ldg(c2 + q); c[2 * q] = v.x; c[2 * q + 1] = v.y; }
     }
-    double p0 = c[kRtDeg], p1 = 0.0, p2 = 0.0, p3 = 0.0;
-#pragma unroll
-    for (int m = kRtDeg - 1; m >= 0; --m) {
-        p3 = fma(p3, t, p2); p2 = fma(p2, t, p1); p1 = fma(p1, t, p0); p0 = fma(p0, t, c[m]);
-    }
-    f[0] = p0; f[1] = p1; f[2] = 2.0 * p2; f[3] = 6.0 * p3;
+    radial_horner<3>(c, t, f);
     return true;
 }
 
@@ -322,11 +317,15 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                 }
                 // ---- K u (for gDelta' = -u^T J): row sums over the quad, from the K at the stage input ------------------
                 double ku = 0.0;
+                {
+                    double ku1 = 0.0;
 #pragma unroll
-                for (int rb = 0; rb < NB; ++rb) {
-                    const double2 uv = *reinterpret_cast<const double2*>(U + 8 * rb + 2 * t4);
-                    ku = fma(Kr[rb][0], uv.x, ku);
-                    ku = fma(Kr[rb][1], uv.y, ku);
+                    for (int rb = 0; rb < NB; ++rb) {
+                        const double2 uv = *reinterpret_cast<const double2*>(U + 8 * rb + 2 * t4);
+                        ku = fma(Kr[rb][0], uv.x, ku);
+                        ku1 = fma(Kr[rb][1], uv.y, ku1);
+                    }
+                    ku += ku1;
                 }
 #else
 #pragma unroll
