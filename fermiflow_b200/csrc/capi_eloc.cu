@@ -150,7 +150,11 @@ int launch_eloc5(ff::FlowArgs& a, cudaStream_t st) {
     const long long room = half - (long long)g.total * 8;
     // (at most 256 rows: small walker blocks leave the shared memory to more resident CTAs instead)
     a.rt_cache_nodes = (a.rt_eta != nullptr && room > 0 && !opt(OPT_NO_RT_CACHE)) ? (int)std::min<long long>(room / (8 * ff::kRtPitch), 256) : 0;
-    return launch_eloc_reg(ff::eloc5_kernel<SN, SMU>, g.threads, (size_t)(g.total + a.rt_cache_nodes * ff::kRtPitch) * 8, g.fin_stride, a, st);
+    size_t smem = (size_t)(g.total + a.rt_cache_nodes * ff::kRtPitch) * 8;
+#ifdef FF_DEV_ONE_CTA
+    smem = std::max<size_t>(smem, (size_t)di.smem_sm / 2 + 4096);          // (dev experiment: one resident CTA per SM)
+#endif
+    return launch_eloc_reg(ff::eloc5_kernel<SN, SMU>, g.threads, smem, g.fin_stride, a, st);
 }
 
 // Statically specialised E_loc sweeps (ff_eloc4.cuh; ff_eloc2.cuh under option "eloc_v2" or without the Taylor tables) for the particle numbers of the BASELINE.json configs; anything

@@ -643,10 +643,14 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                     inv_d = rsqrt(d2);
                     dd = d2 * inv_d;
                     double f[4];
-                    if (!radial_eval_mirror(my_rt, rt_cache, it_pair ? ncache : 0, dd, f))
+                    if (radial_eval_mirror(my_rt, rt_cache, it_pair ? ncache : 0, dd, f)) {
+                        f0 = f[0]; f1 = f[1]; f2 = f[2]; f3 = f[3];
+                    } else {            // (its own array: the out-of-line call would pin f to the stack frame on the table path too)
+                        double g[4];
                         radial_direct_global(it_pair ? a.eta_w1 : a.mu_w1, it_pair ? a.eta_b1 : a.mu_b1,
-                                             it_pair ? a.eta_w2 : a.mu_w2, it_pair ? a.H_eta : a.H_mu, dd, f);
-                    f0 = f[0]; f1 = f[1]; f2 = f[2]; f3 = f[3];
+                                             it_pair ? a.eta_w2 : a.mu_w2, it_pair ? a.H_eta : a.H_mu, dd, g);
+                        f0 = g[0]; f1 = g[1]; f2 = g[2]; f3 = g[3];
+                    }
                 }
                 E5T(6);
                 named_bar_sync(4, NT);

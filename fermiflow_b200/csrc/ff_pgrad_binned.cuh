@@ -24,7 +24,10 @@
 
 namespace ff {
 
-constexpr int kPgMaxBins = 640;          // eta bins + mu bins = threads of the CTA (96 registers each)
+#ifndef FF_PG_BINS
+#define FF_PG_BINS 640
+#endif
+constexpr int kPgMaxBins = FF_PG_BINS;          // eta bins + mu bins = threads of the CTA (96 registers each)
 constexpr int kPgMom = 12;               // moments per weight (t^0 .. t^11): 48 accumulator registers per thread
 constexpr double kPgSpacing = 0.25;      // delta * max|w1|: truncation (0.125 / pi)^12 ~ 2e-17
 constexpr double kPgDmax = 24.0;         // node range of the pair distances (beyond: direct evaluation in the kernel)
@@ -153,7 +156,7 @@ __device__ unsigned long long g_pg_maxbin[4];
 #define PGT(seg) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(kPgMaxBins, 1) pgrad_binned_kernel(const PGradBinArgs a) {
+__global__ void __launch_bounds__(kPgMaxBins, kPgMaxBins <= 320 ? 2 : 1) pgrad_binned_kernel(const PGradBinArgs a) {
     extern __shared__ __align__(16) double smem[];
     const double* hdr = a.work;
     if (hdr[6] == 0.0) return;                                   // bins do not fit: pgrad_kernel runs instead

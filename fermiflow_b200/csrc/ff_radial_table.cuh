@@ -103,13 +103,17 @@ __global__ void __launch_bounds__(128) radial_table_build_kernel(const RadialBui
 
 // The first ORD + 1 of f, f', f'', f''' of the expansion with coefficients c at offset t: Horner in four running sums.
 // The sums of the derivatives start at zero, so their first steps are copies (fma(0, t, p) = p: 6 of the 44 instructions
-// at ORD 3, the same values bit for bit).
+// at ORD 3, the same values bit for bit).  The node spacing (|t| <= 0.075 / max|w1|) is set by the third derivative: the
+// relative size of the term of degree m is 0.0239^m in f and m 0.0239^(m-1) in f', so the value-only sweeps stop at
+// degree kRtDeg - 2 (first dropped term 6e-17 of the scale of f) and the value + derivative sweeps at kRtDeg - 1
+// (7e-16 of the scale of f'); their top coefficients are never loaded.
 template <int ORD>
 __device__ __forceinline__ void radial_horner(const double (&c)[kRtCoef], double t, double (&f)[4]) {
-    double p0 = c[kRtDeg], p1 = 0.0, p2 = 0.0, p3 = 0.0;
+    constexpr int TOP = kRtDeg - (ORD == 0 ? 2 : ORD == 1 ? 1 : 0);
+    double p0 = c[TOP], p1 = 0.0, p2 = 0.0, p3 = 0.0;
 #pragma unroll
-    for (int m = kRtDeg - 1; m >= 0; --m) {
-        const int it = kRtDeg - 1 - m;
+    for (int m = TOP - 1; m >= 0; --m) {
+        const int it = TOP - 1 - m;
         if (ORD >= 3) p3 = it >= 3 ? fma(p3, t, p2) : p2;
         if (ORD >= 2) p2 = it >= 2 ? fma(p2, t, p1) : p1;
         if (ORD >= 1) p1 = it >= 1 ? fma(p1, t, p0) : p0;
