@@ -237,7 +237,8 @@ int ff_eloc(const ff_model* m, const double* x, long long B, const int* orb, con
     if (stash_c && !stash_y) return fail(-1, "ff_eloc: stash_c needs stash_y");
     ff::FlowArgs a{};
     int threads; size_t smem;
-    if (int e = plan_flow(ff::MODE_ELOC, m, a, threads, smem)) return e;
+    bool jglobal = false;
+    if (int e = plan_flow(ff::MODE_ELOC, m, a, threads, smem, jglobal)) return e;
     a.ta = m->t1; a.tb = m->t0;
     a.B = B; a.x_in = x; a.y_out = z; a.delta_out = delta_logp;
     a.stash_y = stash_y; a.stash_c = stash_c;
@@ -249,6 +250,16 @@ int ff_eloc(const ff_model* m, const double* x, long long B, const int* orb, con
         ff::FlowArgs a2 = a;
         const int r = try_eloc_static(a2, (cudaStream_t)stream);
         if (r != FF_FALLBACK) return r;
+    }
+    // particle numbers beyond the shared-memory budget (n > 26): RK partials of J in a stream-ordered global scratch,
+    // one slot per walker of every CTA the device can hold
+    struct Scratch { double* p = nullptr; cudaStream_t s = nullptr; ~Scratch() { if (p) cudaFreeAsync(p, s); } } scratch;
+    if (jglobal) {
+        const DevInfo di = dev_info();
+        const long long ctas = (long long)di.sms * std::max<long long>(1, (long long)di.smem_sm / (long long)smem);
+        scratch.s = (cudaStream_t)stream;
+        FF_CUDA(cudaMallocAsync((void**)&scratch.p, (size_t)ctas * a.W * 4 * a.D * a.D * sizeof(double), scratch.s));
+        a.jpart = scratch.p;
     }
     return launch_flow<ff::MODE_ELOC>(a, threads, smem, (cudaStream_t)stream);
 }

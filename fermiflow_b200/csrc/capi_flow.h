@@ -17,7 +17,13 @@ struct RadialTables {
 };
 
 // Fills the geometry fields of FlowArgs and returns threads / dynamic smem bytes.
+inline int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t& smem, bool& jglobal);
 inline int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t& smem) {
+    bool jglobal = false;
+    return plan_flow(mode, m, a, threads, smem, jglobal);
+}
+inline int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads, size_t& smem, bool& jglobal) {
+    jglobal = false;
     const DevInfo di = dev_info();
     const int n = m->n_up + m->n_dn;
     a.n = n; a.n_up = m->n_up; a.H_eta = m->H_eta; a.H_mu = m->H_mu;
@@ -25,14 +31,22 @@ inline int plan_flow(int mode, const ff_model* m, ff::FlowArgs& a, int& threads,
     a.mu_w1 = m->mu_w1; a.mu_b1 = m->mu_b1; a.mu_w2 = m->mu_w2;
     a.nsteps = m->nsteps;
     const bool eloc = mode == ff::MODE_ELOC;
-    const ff::FlowGeom g = ff::flow_geom(mode, n, m->H_mu > 0);
+    ff::FlowGeom g = ff::flow_geom(mode, n, m->H_mu > 0);
+    const int fin_need = eloc ? ff::slater_scratch_size(m->n_up, m->n_dn) + 2 * g.D + n * n + g.NP + 8 : 0;
+    a.jpart = nullptr;
+    if (eloc) {
+        // a walker whose blocks do not fit in shared memory keeps the RK partials of J in global memory (the caller
+        // allocates FlowArgs::jpart when jglobal comes back set)
+        int common0 = ff::kTabDoubles + 6 * (((m->H_eta + 3) & ~3) + ((m->H_mu + 3) & ~3));
+        common0 = even(common0) + 2 * ((g.NP + 7) / 8) + 2;
+        if ((long long)di.smem_optin / 8 - common0 < g.wstride) { g = ff::flow_geom(mode, n, m->H_mu > 0, true, even(fin_need)); jglobal = true; }
+    }
     a.D = g.D; a.NP = g.NP; a.P = g.P; a.DP = g.DP; a.NV = g.NV; a.NSV = g.NSV; a.NPAR = g.NPAR; a.grec = g.grec;
     a.off_G = g.off_G; a.off_AM = g.off_AM; a.off_u = g.off_u; a.off_kLx = g.off_kLx; a.off_part = g.off_part;
     a.off_x0 = g.off_x0; a.off_sl = g.off_sl; a.wstride = g.wstride;
     if (a.P < 1) return fail(-1, "a single particle without one-body backflow has no velocity field");
     if (eloc) {
-        const int need = ff::slater_scratch_size(m->n_up, m->n_dn) + 2 * a.D + n * n + a.NP + 8;
-        if (need > 4 * a.NPAR) return fail(-2, "internal: finale scratch does not fit");
+        if (fin_need > g.off_G - g.NSV) return fail(-2, "internal: finale scratch does not fit");
     }
     int common = ff::kTabDoubles + 6 * (((m->H_eta + 3) & ~3) + ((m->H_mu + 3) & ~3));
     common = even(common) + 2 * ((a.NP + 7) / 8) + 2;

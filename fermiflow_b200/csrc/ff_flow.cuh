@@ -55,6 +55,9 @@ struct FlowArgs {
     int wstride;            // shared doubles per walker
     int grec;               // doubles per item record (kGRec for MODE_ELOC, 3 otherwise: vx, vy, q)
     int off_G, off_AM, off_u, off_kLx, off_part, off_x0, off_sl;   // offsets inside a walker block
+    // generic E_loc sweep for particle numbers whose Jacobian blocks do not all fit in shared memory (n > 26): the three RK
+    // partials of J and its stage derivative live in global memory instead, 4 D^2 doubles per resident walker (L2 resident)
+    double* jpart;
 };
 
 // State vector layout (MODE_ELOC): [y:D][L:D][gD:D][Delta, lapDelta][J: D x DP]
@@ -66,7 +69,7 @@ struct FlowGeom {
     int off_G, off_AM, off_u, off_kLx, off_part, off_x0, off_sl, wstride, threads1;
 };
 __host__ __device__ constexpr int ff_even(int x) { return (x + 1) & ~1; }
-__host__ __device__ constexpr FlowGeom flow_geom(int mode, int n, bool has_mu) {
+__host__ __device__ constexpr FlowGeom flow_geom(int mode, int n, bool has_mu, bool jglobal = false, int scratch_min = 0) {
     FlowGeom g{};
     const bool eloc = mode == MODE_ELOC;
     g.n = n; g.D = 2 * n; g.D8 = (g.D + 7) & ~7;
@@ -74,9 +77,10 @@ __host__ __device__ constexpr FlowGeom flow_geom(int mode, int n, bool has_mu) {
     g.DP = eloc ? g.D8 + 4 : g.D;                 // DP mod 16 in {4, 12}: conflict-free DMMA fragments
     g.NV = eloc ? 3 * g.D + 2 : g.D + (mode >= MODE_DIV ? 1 : 0);
     g.NSV = eloc ? ff_even(g.NV + g.D8 * g.DP) : g.NV;
-    g.NPAR = eloc ? ff_even(g.NV + g.D * g.D) : g.NV;
+    // (jglobal: the J parts of the RK partials are in FlowArgs::jpart; the area still holds the scratch of the finale)
+    g.NPAR = eloc ? (jglobal ? ff_even(g.NV) : ff_even(g.NV + g.D * g.D)) : g.NV;
     g.grec = eloc ? kGRec : 3;
-    int off = ff_even(g.NSV + 4 * g.NPAR);
+    int off = ff_even(g.NSV + (jglobal && 4 * g.NPAR < scratch_min ? scratch_min : 4 * g.NPAR));
     g.off_G = off; off = ff_even(off + g.P * g.grec);
     g.off_AM = off; if (eloc) off = ff_even(off + g.D8 * g.DP);
     g.off_u = off; if (eloc) off += g.D;
@@ -386,6 +390,11 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
     const int oDelta = (MODE == MODE_ELOC) ? oS : D;
     const int NV = kS ? GS.NV : a.NV, NPAR = kS ? GS.NPAR : a.NPAR;
     const int oP3 = NSV, oP4 = NSV + NPAR, oPO = NSV + 2 * NPAR, oK = NSV + 3 * NPAR;
+    // J part (D x D, unpadded) of RK block `which` (0: P3, 1: P4, 2: PO, 3: stage derivative) of walker w of this CTA
+    double* const jglob = (MODE == MODE_ELOC && !kS) ? a.jpart : nullptr;
+    auto jblock = [&](double* Sw, int w, int which) -> double* {
+        return jglob ? jglob + (((size_t)blockIdx.x * W + w) * 4 + which) * (size_t)(D * D) : Sw + NSV + which * NPAR + NV;
+    };
 
     GramPlan gplan;
     const int item_warps = (W * P + 31) >> 5;
@@ -614,7 +623,7 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
                         dmma_chunk(D8, nch, [&](int k) { return Ap[k]; },
                                    [&](int c, int k) { return Bp[k * DP + 8 * c]; }, acc);
                         // derivative block keeps J unpadded: [D][D]
-                        double* K = Sw + oK + NV + (8 * rb + g) * D + 8 * cb0 + 2 * t;
+                        double* K = jblock(Sw, w, 3) + (8 * rb + g) * D + 8 * cb0 + 2 * t;
                         if (8 * rb + g < D) {
 #pragma unroll
                             for (int c = 0; c < kCH; ++c)
@@ -704,13 +713,13 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
                 if (MODE == MODE_ELOC) {
                     // J: state rows have stride DP, partial rows stride D
                     const int hD = D >> 1;
-                    auto updJ = [&](double* Sw, int r, int c) {
+                    auto updJ = [&](double* Sw, int w, int r, int c) {
                         double2* s2 = reinterpret_cast<double2*>(Sw + NV + r * DP + c);
-                        const int pe = NV + r * D + c;
-                        double2* p3 = reinterpret_cast<double2*>(Sw + oP3 + pe);
-                        double2* p4 = reinterpret_cast<double2*>(Sw + oP4 + pe);
-                        double2* po = reinterpret_cast<double2*>(Sw + oPO + pe);
-                        double2 k = *reinterpret_cast<const double2*>(Sw + oK + pe);
+                        const int pe = r * D + c;
+                        double2* p3 = reinterpret_cast<double2*>(jblock(Sw, w, 0) + pe);
+                        double2* p4 = reinterpret_cast<double2*>(jblock(Sw, w, 1) + pe);
+                        double2* po = reinterpret_cast<double2*>(jblock(Sw, w, 2) + pe);
+                        double2 k = *reinterpret_cast<const double2*>(jblock(Sw, w, 3) + pe);
                         k.x *= h; k.y *= h;
                         if (sub == 0) {
                             const double2 y0 = *s2;
@@ -737,7 +746,7 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
                         for (int wr = warp; wr < W * D; wr += nwarp) {
                             const int w = kS ? 0 : wr / D, r = wr - w * D;
                             double* Sw = wbase + (size_t)w * wstride;
-                            for (int c2 = lane; c2 < hD; c2 += 32) updJ(Sw, r, 2 * c2);
+                            for (int c2 = lane; c2 < hD; c2 += 32) updJ(Sw, w, r, 2 * c2);
                         }
                     } else {
                         // short rows (small n, many walkers per CTA): flat over (walker, row, column pair)
@@ -745,7 +754,7 @@ __device__ __forceinline__ void flow_body(const FlowArgs& a) {
                         for (int q = tid; q < W * per; q += T) {
                             const int w = q / per, rc = q - w * per;
                             const int r = rc / hD, c2 = rc - r * hD;
-                            updJ(wbase + (size_t)w * wstride, r, 2 * c2);
+                            updJ(wbase + (size_t)w * wstride, w, r, 2 * c2);
                         }
                     }
                 }

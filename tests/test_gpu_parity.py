@@ -232,6 +232,9 @@ CASES = [  # nup, ndown, H_eta, H_mu, nsteps, batch
     (5, 5, 8, 8, 4, 3),         # register-resident sweep at the other particle numbers from 10 on: N = 10 (D8 = 24: padded blocks)
     (7, 6, 10, 10, 4, 3),       # N = 13 (D = 26 in four row blocks)
     (9, 8, 8, 8, 2, 2),         # N = 17 (D = 34 in five row blocks)
+    (11, 11, 8, 8, 2, 2),       # N = 22: beyond the register-resident sweep, generic flow_kernel<MODE_ELOC>, blocks in shared memory
+    (14, 14, 8, 6, 2, 2),       # N = 28: RK partials of the Jacobian in global scratch (FlowArgs::jpart)
+    (16, 15, 6, 6, 2, 2),       # N = 31: the largest the item-per-thread sweeps take with a one-body term (496 items)
 ]
 
 
