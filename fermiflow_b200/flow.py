@@ -168,6 +168,31 @@ class CNF(torch.nn.Module):
         print("MaxAbs of logp_inverse - logp:", dlp)
         return float(dz), float(dlp), float((x2 - x).abs().max())
 
+    def calibrate_nsteps(self, x, rtol=1e-6, atol=1e-8, min_nsteps=2, max_nsteps=512):
+        """Tolerance-driven choice of the fixed grid (the reference integrates with torchdiffeq's adaptive dopri5 at
+        rtol 1e-6 / atol 1e-8, nnModule.py:161-162; here every walker takes the same `nsteps` RK4 steps).  Step doubling
+        on the sample `x` ([batch, n, 2]): the smallest power-of-two multiple of `min_nsteps` whose (z, delta_logp) agree
+        with the result of twice as many steps in torchdiffeq's mixed norm, rms(err / (atol + rtol max(|a|, |b|))) <= 1,
+        scaled by 16 / 15 (Richardson: the coarser result carries 16 / 15 of the difference at fourth order).
+        Sets and returns self.nsteps; raises if max_nsteps does not reach the tolerance."""
+        def norm(a, b):
+            tol = atol + rtol * torch.maximum(a.abs(), b.abs())
+            return float(((a - b) / tol).pow(2).mean().sqrt()) * 16.0 / 15.0
+        keep, ns = self.nsteps, int(min_nsteps)
+        try:
+            self.nsteps = ns
+            z0, d0 = self.delta_logp(x)
+            while 2 * ns <= max_nsteps:
+                self.nsteps = 2 * ns
+                z1, d1 = self.delta_logp(x)
+                if max(norm(z0, z1), norm(d0, d1)) <= 1.0:
+                    keep = ns
+                    return ns
+                ns, z0, d0 = 2 * ns, z1, d1
+            raise RuntimeError("CNF.calibrate_nsteps: %d RK4 steps do not reach rtol %g / atol %g" % (max_nsteps, rtol, atol))
+        finally:
+            self.nsteps = keep
+
     def delta_logp(self, x, params_require_grad=False):  # flow.py:52-56
         params = _flat_params(self.v) if params_require_grad else []
         return _DeltaLogp.apply(self, x, params_require_grad, *params)

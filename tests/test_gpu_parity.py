@@ -839,6 +839,28 @@ def test_generate_trajectory_frames_and_reversibility_check(dev, O):
     assert dz < 1e-6 and dlp < 1e-5 and dx < 1e-12
 
 
+def test_calibrate_nsteps_meets_the_reference_tolerance(dev, O):
+    """CNF.calibrate_nsteps: the fixed grid chosen by step doubling at the reference's default tolerance (rtol 1e-6,
+    atol 1e-8, nnModule.py:161-162) reproduces a 256-step solve of the oracle within that tolerance, a tighter request
+    picks a finer grid, and an unreachable one raises with nsteps left untouched."""
+    from fermiflow_b200 import Backflow, CNF
+    eta, mu = rand_mlp(12, 3, 0.3, dev), rand_mlp(9, 4, 0.3, dev)
+    cnf = CNF(Backflow(eta, mu=mu), (0.0, 1.0), nsteps=16)
+    x = 0.9 * torch.randn(64, 6, 2, generator=torch.Generator().manual_seed(8)).to(dev)
+    ns = cnf.calibrate_nsteps(x)
+    assert ns == cnf.nsteps and 2 <= ns <= 64
+    z, dl = cnf.delta_logp(x)
+    zr, dlr = O.cnf_delta_logp(x.cpu(), cpu_params(eta), cpu_params(mu), (0.0, 1.0), 256)
+    tol = lambda r: 1e-8 + 1e-6 * r.abs()
+    assert float(((z.cpu() - zr) / tol(zr)).pow(2).mean().sqrt()) <= 1.0
+    assert float(((dl.cpu() - dlr) / tol(dlr)).pow(2).mean().sqrt()) <= 1.0
+    ns_tight = cnf.calibrate_nsteps(x, rtol=1e-10, atol=1e-12)
+    assert ns_tight > ns
+    with pytest.raises(RuntimeError):
+        cnf.calibrate_nsteps(x, rtol=1e-15, atol=1e-17, max_nsteps=8)
+    assert cnf.nsteps == ns_tight
+
+
 def test_eloc_static_kernel_spin_polarised_many_walkers_per_cta(dev):
     """Spin-polarised N = 12 (BASELINE config 3): the statically specialised sweep keeps its finale scratch partly
     in the dead J1 buffer and re-zeroes it; with ~7 walkers per CTA it must agree with the generic kernel
