@@ -156,6 +156,18 @@ __device__ unsigned long long g_pg_maxbin[4];
 #define PGT(seg) do { } while (0)
 #endif
 
+// Slots per bin and tile (unsigned short record ids).  A tile is R walkers x ONE stage, so the records of a tile fall into
+// the bins like independent draws (mean ~10 per eta bin at R = 28, 20 in the densest bins); a record that finds its bin
+// full joins the records outside the node range and is summed directly.
+constexpr int kPgCap = 40;
+__host__ __device__ inline size_t pgrad_binned_smem_bytes(int R, int P, int D, int NP) {
+    const size_t REC = (size_t)R * P;
+    return 8 * ((size_t)kTabDoubles + 2 * (size_t)R * 2 * D + 2 * ((R + 1) & ~1) + 3 * REC)     // tab, (y, kbar) x 2, kd x 2, (t, A, B)
+           + 4 * ((size_t)kPgMaxBins + 8)                                                     // fill counters, overflow counters
+           + 2 * ((size_t)kPgMaxBins * kPgCap + ((REC + 3) & ~(size_t)3))                        // slot lists, overflow list
+           + 2 * (size_t)((NP + 7) & ~7) + 64;
+}
+
 __global__ void __launch_bounds__(kPgMaxBins, kPgMaxBins <= 320 ? 2 : 1) pgrad_binned_kernel(const PGradBinArgs a) {
     extern __shared__ __align__(16) double smem[];
     const double* hdr = a.work;
@@ -167,6 +179,7 @@ __global__ void __launch_bounds__(kPgMaxBins, kPgMaxBins <= 320 ? 2 : 1) pgrad_b
     const double inv_de = hdr[0], de = hdr[1], inv_dm = hdr[3], dm = hdr[4];
     const int nb_e = (int)hdr[2], nb_m = (int)hdr[5], nbins = nb_e + nb_m;
     const int REC = R * P;
+    (void)warp;
     // shared carve-up
     double* tab = smem;                                   // kTabDoubles (direct evaluation of overflow records)
     double* ysk0 = tab + kTabDoubles;                     // 2 buffers of R x 2D (next tile arrives by cp.async)
@@ -174,16 +187,12 @@ __global__ void __launch_bounds__(kPgMaxBins, kPgMaxBins <= 320 ? 2 : 1) pgrad_b
     double* rec_t = kdl0 + 2 * ((R + 1) & ~1);            // REC each
     double* rec_A = rec_t + REC;
     double* rec_B = rec_A + REC;
-    int* cnt = reinterpret_cast<int*>(rec_B + REC);       // kPgMaxBins
-    int* off = cnt + kPgMaxBins;
-    int* cur = off + kPgMaxBins;
-    int* wsum = cur + kPgMaxBins;                         // 32 warp totals + 2 counters
-    unsigned short* rec_bin = reinterpret_cast<unsigned short*>(wsum + 40);
-    unsigned short* sorted = rec_bin + ((REC + 3) & ~3);
-    unsigned short* ovf = sorted + ((REC + 3) & ~3);
+    int* cur = reinterpret_cast<int*>(rec_B + REC);       // kPgMaxBins: records of this tile in each bin
+    int* ovf_counts = cur + kPgMaxBins;                   // one counter per tile parity (8 ints reserved)
+    unsigned short* slots = reinterpret_cast<unsigned short*>(ovf_counts + 8);     // kPgMaxBins x kPgCap
+    unsigned short* ovf = slots + (size_t)kPgMaxBins * kPgCap;
     unsigned char* pair_i = reinterpret_cast<unsigned char*>(ovf + ((REC + 3) & ~3));
     unsigned char* pair_j = pair_i + ((NP + 7) & ~7);
-    int* ovf_counts = wsum + 32;                          // one counter per tile parity
 
     fill_exp_table(tab);
     const double* tabl = tab + (tid & 15);
@@ -211,31 +220,42 @@ __global__ void __launch_bounds__(kPgMaxBins, kPgMaxBins <= 320 ? 2 : 1) pgrad_b
 #ifdef FF_PG_TIMING
     long long tprev = clock64();
 #endif
-    const long long nrec = a.B * NS;
+    // tile tix = (stage, block of R walkers): local row r is walker w0 + r at that stage
+    const long long wblocks = (a.B + R - 1) / R, ntiles = wblocks * NS;
+    auto tile_rows = [&](long long tix, long long& w0, int& stage) -> int {
+        const long long wb = tix / NS;
+        w0 = wb * R; stage = (int)(tix - wb * NS);
+        return (int)min((long long)R, a.B - w0);
+    };
     // stage-input / adjoint rows of one tile, asynchronously (cp.async) into buffer `buf`
-    auto fetch_tile = [&](long long r0, int buf) {
-        if (r0 >= nrec) return;
-        const int nr = (int)min((long long)R, nrec - r0);
+    auto fetch_tile = [&](long long tix, int buf) {
+        if (tix >= ntiles) return;
+        long long w0; int stage;
+        const int nr = tile_rows(tix, w0, stage);
         double* yb = ysk0 + (size_t)buf * R * 2 * D;
-        for (int g = tid; g < nr * 2 * D; g += T) {
-            const int r = g / (2 * D), e = g - r * 2 * D;
-            const double* src = (e < D) ? a.stash_y + (r0 + r) * D + e : a.kbar + (r0 + r) * D + e - D;
+        const int D2 = 2 * D;
+        int r = tid / D2, e = tid - r * D2;                    // (T < 2 * D2 rows per pass: one conditional step per pass)
+        const int dr = T / D2, de_ = T - dr * D2;
+        for (int g = tid; g < nr * D2; g += T) {
+            const long long rr = (w0 + r) * NS + stage;
+            const double* src = (e < D) ? a.stash_y + rr * D + e : a.kbar + rr * D + e - D;
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(yb + g)), "l"(src));
+            r += dr; e += de_;
+            if (e >= D2) { e -= D2; ++r; }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         double* kb = kdl0 + buf * ((R + 1) & ~1);
-        for (int r = tid; r < nr; r += T) {
-            const long long rr = r0 + r;
-            const long long b = rr / NS; const int stage = (int)(rr - b * NS), sb = stage & 3;
-            kb[r] = a.gbar_delta[b] * a.h * ((sb == 0 || sb == 3) ? 0.125 : 0.375);
-        }
+        const int sb = stage & 3;
+        const double wgt = a.h * ((sb == 0 || sb == 3) ? 0.125 : 0.375);
+        for (int q = tid; q < nr; q += T) kb[q] = a.gbar_delta[w0 + q] * wgt;
     };
-    if (tid < nbins) { cnt[tid] = 0; cur[tid] = 0; }
+    if (tid < kPgMaxBins) cur[tid] = 0;
     if (tid < 2) ovf_counts[tid] = 0;
-    fetch_tile((long long)blockIdx.x * R, 0);
+    fetch_tile((long long)blockIdx.x, 0);
     int buf = 0;
-    for (long long r0 = (long long)blockIdx.x * R; r0 < nrec; r0 += (long long)gridDim.x * R, buf ^= 1) {
-        const int nr = (int)min((long long)R, nrec - r0);
+    for (long long tix = blockIdx.x; tix < ntiles; tix += gridDim.x, buf ^= 1) {
+        long long w0_; int stage_;
+        const int nr = tile_rows(tix, w0_, stage_);
         const double* ysk = ysk0 + (size_t)buf * R * 2 * D;
         const double* kdl = kdl0 + buf * ((R + 1) & ~1);
         PGT(0);
@@ -244,83 +264,64 @@ __global__ void __launch_bounds__(kPgMaxBins, kPgMaxBins <= 320 ? 2 : 1) pgrad_b
         PGT(1);
         int* ovf_count = ovf_counts + buf;
         if (tid == 0) ovf_counts[buf ^ 1] = 0;                // for the next tile (last read before the barrier above)
-        // ---- records: d, weights, bin --------------------------------------------------------
-        for (int g = tid; g < nr * P; g += T) {
-            const int r = g / P, p = g - r * P;
-            const double* y = ysk + (size_t)r * 2 * D;
-            const double* k = y + D;
-            const double kd = kdl[r];
-            double rx, ry, kx, ky, A, Bc, d;
-            const bool pr = p < NP;
-            if (pr) {
-                const int i = pair_i[p], j = pair_j[p];
-                rx = y[2 * i] - y[2 * j]; ry = y[2 * i + 1] - y[2 * j + 1];
-                kx = k[2 * i] - k[2 * j]; ky = k[2 * i + 1] - k[2 * j + 1];
-                { const double d2 = fma(rx, rx, ry * ry); d = d2 * rsqrt(d2); }
-                A = fma(kx, rx, ky * ry) - 4.0 * kd; Bc = -2.0 * kd * d;
-            } else {
-                const int i = p - NP;
-                rx = y[2 * i]; ry = y[2 * i + 1]; kx = k[2 * i]; ky = k[2 * i + 1];
-                { const double d2 = fma(rx, rx, ry * ry); d = d2 * rsqrt(d2); }
-                A = fma(kx, rx, ky * ry) - 2.0 * kd; Bc = -kd * d;
-            }
-            const double kf = rint(d * (pr ? inv_de : inv_dm));
-            const int nb = pr ? nb_e : nb_m;
-            rec_A[g] = A; rec_B[g] = Bc;
-            if (kf < (double)nb) {
-                const int bin = (int)kf + (pr ? 0 : nb_e);
-                rec_t[g] = fma(-kf, pr ? de : dm, d);
-                rec_bin[g] = (unsigned short)bin;
-                atomicAdd(&cnt[bin], 1);
-            } else {                                        // outside the node range: direct evaluation below
-                rec_t[g] = d;
-                rec_bin[g] = 0xFFFFu;
-                ovf[atomicAdd(ovf_count, 1)] = (unsigned short)g;
+        // ---- records: d, weights, bin; every record goes straight into the slot list of its bin ----------------
+        {
+            int r = tid / P, p = tid - r * P;                 // g = r P + p advances by T: no division inside the loop
+            const int dr = T / P, dp = T - dr * P;
+            for (int g = tid; g < nr * P; g += T) {
+                const double* y = ysk + (size_t)r * 2 * D;
+                const double* k = y + D;
+                const double kd = kdl[r];
+                double rx, ry, kx, ky, A, Bc, d;
+                const bool pr = p < NP;
+                if (pr) {
+                    const int i = pair_i[p], j = pair_j[p];
+                    const double2 yi = *reinterpret_cast<const double2*>(y + 2 * i), yj = *reinterpret_cast<const double2*>(y + 2 * j);
+                    const double2 ki = *reinterpret_cast<const double2*>(k + 2 * i), kj = *reinterpret_cast<const double2*>(k + 2 * j);
+                    rx = yi.x - yj.x; ry = yi.y - yj.y; kx = ki.x - kj.x; ky = ki.y - kj.y;
+                    { const double d2 = fma(rx, rx, ry * ry); d = d2 * rsqrt(d2); }
+                    A = fma(kx, rx, ky * ry) - 4.0 * kd; Bc = -2.0 * kd * d;
+                } else {
+                    const int i = p - NP;
+                    const double2 yi = *reinterpret_cast<const double2*>(y + 2 * i), ki = *reinterpret_cast<const double2*>(k + 2 * i);
+                    rx = yi.x; ry = yi.y; kx = ki.x; ky = ki.y;
+                    { const double d2 = fma(rx, rx, ry * ry); d = d2 * rsqrt(d2); }
+                    A = fma(kx, rx, ky * ry) - 2.0 * kd; Bc = -kd * d;
+                }
+                const double kf = rint(d * (pr ? inv_de : inv_dm));
+                const int nb = pr ? nb_e : nb_m;
+                rec_A[g] = A; rec_B[g] = Bc;
+                bool placed = false;
+                if (kf < (double)nb) {
+                    const int bin = (int)kf + (pr ? 0 : nb_e);
+                    const int pos = atomicAdd(&cur[bin], 1);
+                    if (pos < kPgCap) {
+                        rec_t[g] = fma(-kf, pr ? de : dm, d);
+                        slots[bin * kPgCap + pos] = (unsigned short)g;
+                        placed = true;
+                    }
+                }
+                if (!placed) {                                  // outside the node range, or its bin is full: direct evaluation below
+                    rec_t[g] = d;
+                    ovf[atomicAdd(ovf_count, 1)] = (unsigned short)g;
+                }
+                r += dr; p += dp;
+                if (p >= P) { p -= P; ++r; }
             }
         }
         PGT(2);
         __syncthreads();
         PGT(3);
-        fetch_tile(r0 + (long long)gridDim.x * R, buf ^ 1);   // overlaps the scan, scatter and bin walk below
-        // ---- exclusive scan of the bin counts ---------------------------------------------------
-        {
-            const int c = tid < nbins ? cnt[tid] : 0;
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            if (lane == 31) wsum[warp] = incl;
-            __syncthreads();
-            if (warp == 0) {
-                int w = lane < (T >> 5) ? wsum[lane] : 0;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
-                wsum[lane] = w;                                 // inclusive warp totals
-            }
-            __syncthreads();
-            if (tid < nbins) off[tid] = incl - c + (warp ? wsum[warp - 1] : 0);
-        }
-        __syncthreads();
-        for (int g = tid; g < nr * P; g += T) {
-            const int bin = rec_bin[g];
-            if (bin != 0xFFFF) sorted[off[bin] + atomicAdd(&cur[bin], 1)] = (unsigned short)g;
-        }
-        __syncthreads();
+        fetch_tile(tix + gridDim.x, buf ^ 1);                 // overlaps the bin walk below
         PGT(4);
-#ifdef FF_PG_TIMING
-        {   // statistics outside the timed segments: per warp the largest bin of this tile
-            unsigned long long c = my_bin < nbins ? cnt[my_bin] : 0;
-            for (int o = 16; o > 0; o >>= 1) { unsigned long long v = __shfl_xor_sync(0xffffffffu, c, o); c = v > c ? v : c; }
-            if (lane == 0) { atomicAdd(&g_pg_maxbin[3], c); atomicMax(&g_pg_maxbin[0], c); if (warp == 0) atomicAdd(&g_pg_maxbin[2], 1ull); }
-            tprev = clock64();
-        }
-#endif
         // ---- every thread walks the records of ITS bin, two records in lock-step (the power chain is serial) ---
         if (my_bin < nbins) {
-            const int p0 = off[my_bin], p1 = p0 + cnt[my_bin];
-            cnt[my_bin] = 0; cur[my_bin] = 0;                    // ready for the next tile (only the owner reads them now)
-            int p = p0;
+            const unsigned short* sl = slots + my_bin * kPgCap;
+            const int p1 = min(cur[my_bin], kPgCap);
+            cur[my_bin] = 0;                                     // ready for the next tile (only the owner touches it now)
+            int p = 0;
             for (; p + 2 <= p1; p += 2) {
-                const int g0 = sorted[p], g1 = sorted[p + 1];
+                const int g0 = sl[p], g1 = sl[p + 1];
                 const double t0 = rec_t[g0], A0 = rec_A[g0], B0 = rec_B[g0];
                 const double t1 = rec_t[g1], A1 = rec_A[g1], B1 = rec_B[g1];
                 double pw0 = 1.0, pw1 = 1.0;
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(kPgMaxBins, kPgMaxBins <= 320 ? 2 : 1) pgrad_b
                 }
             }
             if (p < p1) {
-                const int g = sorted[p];
+                const int g = sl[p];
                 const double t = rec_t[g], A = rec_A[g], Bc = rec_B[g];
                 double pw = 1.0;
 #pragma unroll
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(kPgMaxBins, kPgMaxBins <= 320 ? 2 : 1) pgrad_b
             }
         }
         PGT(5);
-        // ---- records outside the node range: direct sums, one hidden unit per thread ----------------
+        // ---- records outside the node range (or beyond a full bin): direct sums, one hidden unit per thread -----------
         const int novf = *ovf_count;
         if (novf > 0 && dir_on) {
             for (int q = 0; q < novf; ++q) {
