@@ -203,9 +203,11 @@ __global__ void __launch_bounds__(kPgMaxBins, kPgMaxBins <= 320 ? 2 : 1) pgrad_b
         pair_j[p] = (unsigned char)(i + 1 + rem);
     }
     // hidden unit of this thread for the direct evaluation of overflow records
-    const bool dir_on = tid < Ht;
-    const bool dir_eta = tid < a.H_eta;
-    const int dir_h = dir_eta ? tid : tid - a.H_eta;
+    // (the threads split into T / Ht slices of the overflow list, one hidden unit each)
+    const int dir_slices = max(1, T / max(Ht, 1)), dir_slice = tid / max(Ht, 1), dir_u = tid - dir_slice * max(Ht, 1);
+    const bool dir_on = dir_slice < dir_slices && Ht > 0;
+    const bool dir_eta = dir_u < a.H_eta;
+    const int dir_h = dir_eta ? dir_u : dir_u - a.H_eta;
     const double dw1 = dir_on ? (dir_eta ? a.eta_w1 : a.mu_w1)[dir_h] : 0.0;
     const double db1 = dir_on ? (dir_eta ? a.eta_b1 : a.mu_b1)[dir_h] : 0.0;
     double s_w2 = 0.0, s_b1 = 0.0, s_w1 = 0.0;
@@ -233,13 +235,14 @@ __global__ void __launch_bounds__(kPgMaxBins, kPgMaxBins <= 320 ? 2 : 1) pgrad_b
         long long w0; int stage;
         const int nr = tile_rows(tix, w0, stage);
         double* yb = ysk0 + (size_t)buf * R * 2 * D;
-        const int D2 = 2 * D;
+        // 16-byte copies: rows of D doubles (D even, the buffers 16-byte aligned), element pairs q of the 2 D-wide local row
+        const int D2 = D, Dh = D >> 1;                         // pairs per local row (y then kbar), pairs per source row
         int r = tid / D2, e = tid - r * D2;                    // (T < 2 * D2 rows per pass: one conditional step per pass)
         const int dr = T / D2, de_ = T - dr * D2;
         for (int g = tid; g < nr * D2; g += T) {
             const long long rr = (w0 + r) * NS + stage;
-            const double* src = (e < D) ? a.stash_y + rr * D + e : a.kbar + rr * D + e - D;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(yb + g)), "l"(src));
+            const double* src = (e < Dh) ? a.stash_y + rr * D + 2 * e : a.kbar + rr * D + 2 * (e - Dh);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(yb + 2 * g)), "l"(src));
             r += dr; e += de_;
             if (e >= D2) { e -= D2; ++r; }
         }
@@ -314,6 +317,14 @@ __global__ void __launch_bounds__(kPgMaxBins, kPgMaxBins <= 320 ? 2 : 1) pgrad_b
         PGT(3);
         fetch_tile(tix + gridDim.x, buf ^ 1);                 // overlaps the bin walk below
         PGT(4);
+#ifdef FF_PG_TIMING
+        {   // statistics outside the timed segments: per warp the fullest bin of this tile
+            unsigned long long c = my_bin < nbins ? (unsigned long long)min(cur[my_bin], kPgCap) : 0;
+            for (int o = 16; o > 0; o >>= 1) { unsigned long long v = __shfl_xor_sync(0xffffffffu, c, o); c = v > c ? v : c; }
+            if (lane == 0) { atomicAdd(&g_pg_maxbin[3], c); atomicMax(&g_pg_maxbin[0], c); if (warp == 0) atomicAdd(&g_pg_maxbin[2], 1ull); }
+            tprev = clock64();
+        }
+#endif
         // ---- every thread walks the records of ITS bin, two records in lock-step (the power chain is serial) ---
         if (my_bin < nbins) {
             const unsigned short* sl = slots + my_bin * kPgCap;
@@ -344,7 +355,7 @@ __global__ void __launch_bounds__(kPgMaxBins, kPgMaxBins <= 320 ? 2 : 1) pgrad_b
         // ---- records outside the node range (or beyond a full bin): direct sums, one hidden unit per thread -----------
         const int novf = *ovf_count;
         if (novf > 0 && dir_on) {
-            for (int q = 0; q < novf; ++q) {
+            for (int q = dir_slice; q < novf; q += dir_slices) {
                 const int g = ovf[q];
                 const int p = g % P;
                 if ((p < NP) != dir_eta) continue;
@@ -371,7 +382,7 @@ __global__ void __launch_bounds__(kPgMaxBins, kPgMaxBins <= 320 ? 2 : 1) pgrad_b
         }
     }
     if (dir_on && (s_w2 != 0.0 || s_b1 != 0.0 || s_w1 != 0.0)) {
-        atomicAdd(direct + 3 * tid, s_w2); atomicAdd(direct + 3 * tid + 1, s_b1); atomicAdd(direct + 3 * tid + 2, s_w1);
+        atomicAdd(direct + 3 * dir_u, s_w2); atomicAdd(direct + 3 * dir_u + 1, s_b1); atomicAdd(direct + 3 * dir_u + 2, s_w1);
     }
 }
 

@@ -114,7 +114,7 @@ int ff_eloc(const ff_model* m, const double* x, long long B, const int* orb, con
 /* Backward of log p = log p0(z) - delta_logp through the flow (the adjoint solve of
  * NeuralODE/nnModule.py:78-103): given upstream gbar_z [B][n][2] and gbar_delta [B] it
  * returns grad_x [B][n][2] (nullable) and ACCUMULATES the parameter gradients into
- * g_eta_* / g_mu_* (same shapes as the parameters).  work: ff_backward_work_size doubles.
+ * g_eta_* / g_mu_* (same shapes as the parameters).  work: ff_backward_work_size doubles; stash_y and work 16-byte aligned.
  * stash_c may be null (see ff_cnf_delta_logp). */
 int ff_logp_backward(const ff_model* m, long long B, const double* stash_y, const double* stash_c,
                      const double* gbar_z, const double* gbar_delta, double* grad_x,

@@ -691,8 +691,11 @@ def test_radial_tables_match_direct_evaluation(dev, case):
         ref = _sweeps(model, z)
     got = _sweeps(model, z)
     for k in ref:
-        close(got[k], ref[k], 2e-12, 1e-13)
-    assert all(torch.isfinite(v).all() for v in got.values())
+        assert torch.isfinite(got[k]).all() and torch.isfinite(ref[k]).all(), "non-finite values in " + k
+        try:
+            close(got[k], ref[k], 2e-12, 1e-13)
+        except AssertionError as e:
+            raise AssertionError("sweep output %r: %s" % (k, e)) from None
 
 
 @pytest.mark.parametrize("case", ["bench", "sharp", "too_sharp", "zero", "far", "far_few", "no_mu"])
