@@ -55,7 +55,8 @@ class FreeFermion(BaseDist):
     torch.manual_seed() controls the chains, as it does for the reference's torch.randn sampler) and advances
     with every call; manual_seed(s) fixes it explicitly.  Under torch.distributed rank r samples the global walkers
     [r B, (r + 1) B): ranks never share a stream, whatever the seed, and a W-rank run of B walkers each draws
-    the same chains as one rank with W B walkers."""
+    the same chains as one rank with W B walkers.  (torch seeds its default generator from the system entropy:
+    without torch.manual_seed or manual_seed the chains differ from process to process, like the reference's.)"""
 
     def __init__(self, device=torch.device("cuda")):
         self.device = torch.device(device)

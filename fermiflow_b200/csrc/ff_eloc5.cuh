@@ -166,6 +166,19 @@ __device__ __forceinline__ bool radial_eval_mirror(const RtHeader& T, const doub
 #ifndef FF_E5_ALITEM
 #define FF_E5_ALITEM 1
 #endif
+// FF_E5_P2P: the two CTA-wide barriers of a stage become point-to-point hand-overs between the owner and the worker group
+// (named barriers with bar.arrive on the producing and bar.sync on the consuming side, each with all NT threads of the CTA
+// as participants), so that neither group waits for the other at a place where it needs nothing from it:
+//   5  items of the stage in place (A off-diagonal, R matrices)      workers arrive, owners sync before their row sums
+//   2  row sums in place (y, u, rho)                                 owners arrive,  workers sync before scalars / next radial functions
+//   6  K A done: A may be overwritten                                owners arrive,  workers sync before the items of the next stage
+//   7  M = K^T K of the stage in place                               owners arrive,  workers sync before the contraction
+//   8  contraction done: M may be overwritten                        workers arrive, owners sync before the next Gram matrix
+// (1: owners only, 3: workers only, 4: whole CTA at the walker boundaries.)  Every hand-over alternates strictly: the
+// producer of one is the consumer of another further round the cycle, so no barrier is armed twice before it completes.
+#ifndef FF_E5_P2P
+#define FF_E5_P2P 1
+#endif
 
 #ifdef FF_E5_TIMING
 __device__ unsigned long long g_e5_cyc[4][16];
@@ -228,6 +241,9 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
             if (tid0 < 8) S[G_.oScal + tid0] = 0.0;
             named_bar_sync(4, NT);
             named_bar_sync(4, NT);                       // (the workers evaluate the radial functions of stage 0)
+#if FF_E5_P2P
+            named_bar_arrive(6, NT);                     // A is free for the items of stage 0
+#endif
 #ifdef FF_E5_TIMING
             const int obs = (tid0 >> 5) == 0 ? 0 : (tid0 >> 5) == 1 ? 1 : -1;
             long long tprev = clock64();
@@ -243,9 +259,17 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                 double* const Y = S + G_.oY;
                 double* const U = S + G_.oU;
                 // ======== phase 1: M = K^T K of this stage ==========================================================
+#if FF_E5_P2P
+                named_bar_sync(8, NT);                // the workers are done with the previous M
+#endif
                 if (warp >= G_.G0 && warp < G_.G0 + G_.GWN) phase_gram5<SN, SMU>(S + G_.oM, Ks, warp - G_.G0, tid & 31);
                 E5T(0);
+#if FF_E5_P2P
+                named_bar_arrive(7, NT);              // M of this stage is in place
+                named_bar_sync(5, NT);                // the items of this stage are in place
+#else
                 named_bar_sync(4, NT);
+#endif
                 E5T(1);
                 // ======== phase 2 ===================================================================================
                 // ---- per-particle sums of this stage: k_y (y advances here), u, rho, diagonal of A -----------------
@@ -351,6 +375,9 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                     }
                 }
                 E5T(4);
+#if FF_E5_P2P
+                if (stage + 1 < NS) named_bar_arrive(6, NT);       // A may be overwritten by the items of the next stage
+#endif
 #if FF_E5_RKACC
                 // ---- the accumulators ARE the new K; shared copy for the Gram matrix of the next stage -----------------
                 ku += __shfl_xor_sync(0xffffffffu, ku, 1);
@@ -388,7 +415,11 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
 #endif
                 gd = rk_elem(sub, gd, -h * ku, gdB, gdC);
                 E5T(5);
+#if FF_E5_P2P
+                named_bar_sync(1, NOWN);              // the shared copy of the new K is complete (owners only)
+#else
                 named_bar_sync(4, NT);
+#endif
                 E5T(7);
             }
             // ---- final state to global memory: gDelta, J = K^T row-major (the workers write the vectors) -----------
@@ -448,6 +479,10 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                 double* const Ln = S + ((stage & 1) ? G_.oL0 : G_.oL1);
                 if (stage >= 0) {
                     // ======== phase 1: the items of this stage from r and the radial functions ======================
+#if FF_E5_P2P
+                    named_bar_sync(6, NT);            // the owners are done with the previous A
+                    E5T(6);
+#endif
                     double ca = 0.0, cb_ = 0.0, ccq = 0.0, ceq = 0.0;
                     if (a.stash_y != nullptr && wl < D) a.stash_y[(b * NS + stage) * D + wl] = Y[wl];
                     if (it_valid) {
@@ -494,7 +529,12 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                         }
                     }
                     E5T(0);
+#if FF_E5_P2P
+                    named_bar_arrive(5, NT);          // the items of this stage are in place
+                    named_bar_sync(7, NT);            // M of this stage is in place
+#else
                     named_bar_sync(4, NT);
+#endif
                     E5T(1);
                     // ======== phase 2 ===============================================================================
                     // ---- contraction of this lane's item with M = J J^T --------------------------------------------
@@ -535,6 +575,9 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                         G2[2] = fma(ccq, trw, ceq * rwr);
                     }
                     E5T(2);
+#if FF_E5_P2P
+                    if (stage + 1 < NS) named_bar_arrive(8, NT);    // M may be overwritten by the next Gram matrix
+#endif
                     named_bar_sync(3, NWRK);
                     // ---- per-particle sums of the contractions: lane (particle wl / 3, component wl % 3) -----------
                     {
@@ -652,9 +695,17 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                         f0 = g[0]; f1 = g[1]; f2 = g[2]; f3 = g[3];
                     }
                 }
+#if FF_E5_P2P
+                E5T(7);
+                if (stage < 0) {
+                    named_bar_sync(4, NT);            // (second barrier of the walker start: the owners wait for stage 0's radial functions)
+                    named_bar_arrive(8, NT);          // M is free for the Gram matrix of stage 0
+                }
+#else
                 E5T(6);
                 named_bar_sync(4, NT);
                 E5T(7);
+#endif
             }
             // ---- final state to global memory: y, L, (Delta, lapDelta) ----------------------------------------------
             {

@@ -14,8 +14,8 @@ lib.ff_debug_e5_cycles.argtypes = [C.POINTER(C.c_ulonglong * 64), C.c_int]
 out = (C.c_ulonglong * 64)()
 model.local_energy(x, stash=True); lib.ff_debug_e5_cycles(C.byref(out), 1)
 model.local_energy(x, stash=True); lib.ff_debug_e5_cycles(C.byref(out), 1)
-names = {0: ["phase 1: Gram (DMMA)", "sync 1", "row sums + y", "bar 1", "K.A (DMMA)", "K.u + RK + Ks", "-", "sync 2"],
-         2: ["phase 1: items", "sync 1", "contraction", "bar 3 + sums", "bar 2", "A.L, L, scalars", "next radial functions", "sync 2"]}
+names = {0: ["wait M free + Gram", "wait items", "row sums + y", "bar 1", "init + K.A (DMMA)", "K.u + Ks copy", "-", "owner barrier"],
+         2: ["items", "wait M", "contraction", "bar 3 + sums + L", "wait row sums", "scalars", "wait A free", "next radial functions"]}
 nb = walkers * 64
 for obs, role in enumerate(["owner warp 0 (no Gram)", "owner warp 1", "first worker warp", "last worker warp"]):
     v = out[16 * obs:16 * obs + 16]

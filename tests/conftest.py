@@ -21,3 +21,13 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+@pytest.fixture(autouse=True)
+def _fixed_seed():
+    """Same inputs in every process: torch seeds its default generator from the system entropy when nothing else is
+    said, and FreeFermion's Metropolis chains (seed = torch.initial_seed() at the first sample()) and every unseeded
+    torch.randn follow it.  A test that wants another seed sets it itself."""
+    import torch
+    torch.manual_seed(int(os.environ.get("FF_TEST_SEED", "20240607")))
+    yield

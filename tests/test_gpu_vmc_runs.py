@@ -70,8 +70,13 @@ def test_energy_statistically_consistent_with_reference_algorithm(dev, nup, ndow
     E, E_std, _ = R.vmc_iteration(nup, ndown, params, True, 2.0, cpu_walkers)
     se_ref = E_std / math.sqrt(cpu_walkers)
     assert abs(e_gpu - E) < 4.0 * math.hypot(se_gpu, se_ref), (e_gpu, se_gpu, E, se_ref)
-    # the two estimates of the spread of E_loc describe the same distribution
-    assert 0.5 < model.E_std / E_std < 2.0, (model.E_std, E_std)
+    # the two estimates of the spread of E_loc describe the same distribution.  E_loc is heavy-tailed (it diverges at the
+    # nodes of the determinants): a few of the 16384 GPU walkers move the sample standard deviation by a factor of three
+    # from seed to seed, the 48 CPU walkers hardly ever see such a walker -- compare the central spread (half the
+    # 16 % - 84 % quantile range, = sigma for a Gaussian) with the CPU standard deviation
+    q = torch.quantile(model.last.eloc, torch.tensor([0.16, 0.84], dtype=torch.float64, device=model.last.eloc.device))
+    spread = float(q[1] - q[0]) / 2.0
+    assert 0.5 < spread / E_std < 2.0, (spread, model.E_std, E_std)
 
 
 def test_readme_finite_temperature_estimators_consistent_with_reference_algorithm(dev):
