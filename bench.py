@@ -90,14 +90,19 @@ class ClockSampler(threading.Thread):
 def flops_per_walker_eloc(n, H_eta, H_mu, ode_steps, tables=True):
     """FP64 flop count of one E_loc sweep per walker (kernel `ff_eloc`).
     Per RK stage: radial functions of the P items + Jacobian GEMM 2 D^3 + Gram matrix 4 n (n+1) D +
-    mat-vecs 4 D^2 + gather 22 n (n-1) + RK update 6 D^2.
-    tables=True  (what the kernel executes): certified degree-11 Taylor tables, 88 flop (Horner for f and
-                 its three derivatives) + 70 flop of geometry per item;
-    tables=False (reference formulation, FF_NO_TABLE=1): 43 flop per item AND hidden unit (sigmoid 21,
-                 pre-activation 2, three derivative factors 8, four accumulations 8, geometry amortised)."""
+    K u 2 D^2 + per-particle sums 22 n (n-1) + RK combinations 3 D^2.
+    tables=True  (what the kernel executes): certified degree-11 Taylor tables, 76 flop (Horner for f and its three
+                 derivatives without the zero steps) + 70 flop of geometry + 22 flop (the item's share of A L) per item;
+                 the RK combination of K is the initial value of the tensor-core accumulators (1.25 FMA per element);
+    tables=False (reference formulation, option no_table): 43 flop per item AND hidden unit (sigmoid 21,
+                 pre-activation 2, three derivative factors 8, four accumulations 8, geometry amortised), A L as a
+                 matrix-vector product, two-partial RK update."""
     D, NP = 2 * n, n * (n - 1) // 2
-    items = (88 + 70) * (NP + (n if H_mu else 0)) if tables else 43 * (NP * H_eta + n * H_mu)
-    per_stage = items + 2 * D ** 3 + 4 * n * (n + 1) * D + 4 * D * D + 22 * n * (n - 1) + 6 * D * D
+    P = NP + (n if H_mu else 0)
+    if tables:
+        per_stage = (76 + 70 + 22) * P + 2 * D ** 3 + 4 * n * (n + 1) * D + 2 * D * D + 22 * n * (n - 1) + 3 * D * D
+    else:
+        per_stage = 43 * (NP * H_eta + n * H_mu) + 2 * D ** 3 + 4 * n * (n + 1) * D + 4 * D * D + 22 * n * (n - 1) + 6 * D * D
     return 4 * ode_steps * per_stage
 
 
@@ -273,14 +278,14 @@ def run_ours(args):
         "gpu_launches": int(launches),     # counted by the library (ff_launch_count) over the timed steps of this rank
         "clocks": sampler.summary(),
         "breakdown_ms": {k: round(v, 2) for k, v in bd.items()},
-        "roofline": {"bound": "fp64", "kernel": "ff_eloc: ff::eloc5_kernel<20,1> (E_loc sweep, 92 % of the call) + ff::eloc_finale_kernel + table build", "achieved": fl / (eloc_ms * 1e-3) / 1e12,
+        "roofline": {"bound": "fp64", "kernel": "ff_eloc: ff::eloc5_kernel<20,1> (E_loc sweep, 97 % of the call) + ff::eloc_finale_warp_kernel + table build", "achieved": fl / (eloc_ms * 1e-3) / 1e12,
                      "peak": peak.value / 1e12, "unit": "TFLOP/s", "frac": fl / (eloc_ms * 1e-3) / peak.value,
                      "peak_source": "ff_fp64_peak DFMA microbenchmark on this device (MEASURED_PEAKS.json has no fp64 entry)",
                      "flops_counted": "executed formulation (radial functions from certified Taylor tables)" if tables_on
                                       else "reference formulation (every hidden unit evaluated)",
-                     # ncu --set full (profiles/r02_eloc5_ncu_full.md): sweep 3.326 GB written + 0.005 GB read, finale
-                     # 0.134 GB read + 0.005 GB written for 9472 walkers
-                     "traffic": 3.4704e9 / 9472 * B if (n == 20 and args.hidden == 50 and args.ode_steps == 16) else None,
+                     # ncu --set full (profiles/r02_eloc5_ncu_full.md, r02_finale_ncu_full.md): sweep 3.324 GB written + 0.004 GB
+                     # read, finale 0.134 GB read + 0.005 GB written for 9472 walkers
+                     "traffic": 3.4663e9 / 9472 * B if (n == 20 and args.hidden == 50 and args.ode_steps == 16) else None,
                      "traffic_source": "ncu dram__bytes_read+write, 9472-walker capture scaled per walker",
                      "kernel_ms": eloc_ms,
                      "hbm": {"achieved": by / (eloc_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

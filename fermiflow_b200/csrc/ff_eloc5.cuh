@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
     constexpr int n = G_.n, D = G_.D, DP = G_.DP, NP = G_.NP, P = G_.P, NB = G_.NB;
     constexpr int NT = G_.threads, OW = G_.OW, WW = G_.WW, NOWN = 32 * OW, NWRK = 32 * WW;
     constexpr int RP = G_.RP, RMAT = G_.RMAT;
+    constexpr int kScalWarp = WW >= 3 ? 2 : WW - 1;       // worker warp that carries Delta and lapDelta
     static_assert(eloc5_supported(SN, SMU != 0), "eloc5_kernel: particle number not supported");
     const int tid0 = threadIdx.x;
     const bool owner0 = tid0 < NOWN;
@@ -581,19 +582,29 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                     named_bar_sync(3, NWRK);
                     // ---- per-particle sums of the contractions: lane (particle wl / 3, component wl % 3) -----------
                     {
-                        const int g2_i = wl / 3, g2_k = wl - 3 * g2_i;
-                        if (g2_i < n) {
-                            const double acc = gather3<SN, SMU>(S + G_.oG2, g2_i, g2_k);
 #if FF_E5_ALITEM
+                        // two lanes per sum when the worker group has them (each takes the partners of one parity: half the
+                        // chain of dependent shared-memory loads and additions)
+                        constexpr bool kSplit = false && 6 * n <= NWRK;      // (measured slower at n = 20: 1890 against 1360 cycles, the predicated halves cost more than the chain)
+                        const int gl = kSplit ? (wl >> 1) : wl, hf = kSplit ? (wl & 1) : 0;
+                        const int g2_i = gl / 3, g2_k = gl - 3 * g2_i;
+                        double acc = 0.0;
+                        if (g2_i < n) acc = kSplit ? gather3_half<SN, SMU>(S + G_.oG2, g2_i, g2_k, hf) : gather3<SN, SMU>(S + G_.oG2, g2_i, g2_k);
+                        if (kSplit) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                        if (g2_i < n && hf == 0) {
                             // components 0, 1 are k_L = A L + (d2v : M) complete (see FF_E5_ALITEM): L advances here
                             if (g2_k < 2) {
                                 const int m = 2 * g2_i + g2_k;
                                 Ln[m] = rk_elem(sub, Lc[m], h * acc, S[G_.oLB + m], S[G_.oLC + m]);
                             } else S[G_.oP2 + g2_i] = acc;
-#else
-                            if (g2_k < 2) S[G_.oKLx + 2 * g2_i + g2_k] = acc; else S[G_.oP2 + g2_i] = acc;
-#endif
                         }
+#else
+                        const int g2_i = wl / 3, g2_k = wl - 3 * g2_i;
+                        if (g2_i < n) {
+                            const double acc = gather3<SN, SMU>(S + G_.oG2, g2_i, g2_k);
+                            if (g2_k < 2) S[G_.oKLx + 2 * g2_i + g2_k] = acc; else S[G_.oP2 + g2_i] = acc;
+                        }
+#endif
                     }
                     E5T(3);
                     named_bar_sync(2, NT);                // the owners' sums of this stage are in place: y, A, u, rho
@@ -663,10 +674,11 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                     // Delta' = -rho, lapDelta' = -(sum_i part2_i + u.L): the RK combination is linear, so lane i < n carries
                     // the share of particle i through all stages in registers and the shares meet once, after the sweep
                     // (a per-stage warp reduction was a 25-deep FP64 chain on the critical path of the workers)
-                    if (wl < n) {
-                        const double rho = S[G_.oP1 + wl];
-                        const double2 uv = *reinterpret_cast<const double2*>(U + 2 * wl), lv = *reinterpret_cast<const double2*>(Lc + 2 * wl);
-                        const double lp = fma(uv.x, lv.x, fma(uv.y, lv.y, S[G_.oP2 + wl]));
+                    // (on worker warp kScalWarp: the first warps carry the per-particle sums)
+                    if (const int sl = wl - 32 * kScalWarp; sl >= 0 && sl < n) {
+                        const double rho = S[G_.oP1 + sl];
+                        const double2 uv = *reinterpret_cast<const double2*>(U + 2 * sl), lv = *reinterpret_cast<const double2*>(Lc + 2 * sl);
+                        const double lp = fma(uv.x, lv.x, fma(uv.y, lv.y, S[G_.oP2 + sl]));
                         sDl = rk_elem(sub, sDl, -h * rho, sDlB, sDlC);
                         sLd = rk_elem(sub, sLd, -h * lp, sLdB, sLdC);
                     }
@@ -715,14 +727,15 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                     F[e] = S[G_.oY + e]; F[D + e] = S[G_.oL0 + e];       // NS is even: L ends in buffer 0
                     if (a.y_out) a.y_out[b * D + e] = S[G_.oY + e];
                 }
-                if ((tid0 >> 5) == OW) {          // the per-particle shares of Delta and lapDelta (n <= 32 lanes of this warp)
-                    double dl = wl < n ? sDl : 0.0, ld = wl < n ? sLd : 0.0;
+                if ((tid0 >> 5) == OW + kScalWarp) {          // the per-particle shares of Delta and lapDelta (n <= 32 lanes of this warp)
+                    const int sl = wl - 32 * kScalWarp;
+                    double dl = sl < n ? sDl : 0.0, ld = sl < n ? sLd : 0.0;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
                         dl += __shfl_xor_sync(0xffffffffu, dl, o);
                         ld += __shfl_xor_sync(0xffffffffu, ld, o);
                     }
-                    if (wl == 0) {
+                    if (sl == 0) {
                         F[3 * D] = dl; F[3 * D + 1] = ld;
                         if (a.delta_out) a.delta_out[b] = dl;
                     }
