@@ -480,11 +480,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                 double* const Ln = S + ((stage & 1) ? G_.oL0 : G_.oL1);
                 if (stage >= 0) {
                     // ======== phase 1: the items of this stage from r and the radial functions ======================
-#if FF_E5_P2P
-                    named_bar_sync(6, NT);            // the owners are done with the previous A
-                    E5T(6);
-#endif
-                    double ca = 0.0, cb_ = 0.0, ccq = 0.0, ceq = 0.0;
+                    double ca = 0.0, cb_ = 0.0, ccq = 0.0, ceq = 0.0, a00 = 0.0, a01 = 0.0, a11 = 0.0;
                     if (a.stash_y != nullptr && wl < D) a.stash_y[(b * NS + stage) * D + wl] = Y[wl];
                     if (it_valid) {
                         if (a.stash_c != nullptr) {
@@ -503,9 +499,9 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                         // A is stored multiplied by the step factor h c_sub of this sub-stage (see FF_E5_RKACC)
                         const double hs = sub == 0 ? h * (1.0 / 3.0) : sub == 3 ? h * 0.125 : h;
                         const double caS = hs * ca, f0S = hs * f0;
-                        const double a00 = fma(caS * rx, rx, f0S), a01 = caS * rx * ry, a11 = fma(caS * ry, ry, f0S);
+                        a00 = fma(caS * rx, rx, f0S); a01 = caS * rx * ry; a11 = fma(caS * ry, ry, f0S);
 #else
-                        const double a00 = fma(ca * rx, rx, f0), a01 = ca * rx * ry, a11 = fma(ca * ry, ry, f0);
+                        a00 = fma(ca * rx, rx, f0); a01 = ca * rx * ry; a11 = fma(ca * ry, ry, f0);
 #endif
                         const double v0 = f0 * rx, v1 = f0 * ry, v2 = ccq * rx, v3 = ccq * ry, v4 = fma(f1, dd, 2.0 * f0);
                         if (it_pair) {          // both orientations of the pair; off-diagonal blocks of A (row-permuted storage)
@@ -516,15 +512,24 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                             Rij[2 * RMAT] = v2; Rji[2 * RMAT] = -v2;
                             Rij[3 * RMAT] = v3; Rji[3 * RMAT] = -v3;
                             Rij[4 * RMAT] = v4; Rji[4 * RMAT] = v4;
-                            const int i2 = 2 * it_i, j2 = 2 * it_j;
+                        } else {                // one-body item: diagonal of the matrices
+                            double* const Rii = R1 + it_i * (RP + 1);
+                            Rii[0] = v0; Rii[RMAT] = v1; Rii[2 * RMAT] = v2; Rii[3 * RMAT] = v3; Rii[4 * RMAT] = v4;
+                        }
+                    }
+#if FF_E5_P2P
+                    // (the R matrices were free since the owners' row sums; only the blocks of A have to wait for the owners' K A)
+                    named_bar_sync(6, NT);            // the owners are done with the previous A
+                    E5T(6);
+#endif
+                    if (it_valid) {
+                        const int i2 = 2 * it_i, j2 = 2 * it_j;
+                        if (it_pair) {          // off-diagonal blocks of A (row-permuted storage), both orientations
                             *reinterpret_cast<double2*>(A + a_row(i2) * DP + j2) = make_double2(-a00, -a01);
                             *reinterpret_cast<double2*>(A + a_row(i2 + 1) * DP + j2) = make_double2(-a01, -a11);
                             *reinterpret_cast<double2*>(A + a_row(j2) * DP + i2) = make_double2(-a00, -a01);
                             *reinterpret_cast<double2*>(A + a_row(j2 + 1) * DP + i2) = make_double2(-a01, -a11);
-                        } else {                // one-body item: diagonal of the matrices, minus its block in the diagonal slot of A
-                            double* const Rii = R1 + it_i * (RP + 1);
-                            Rii[0] = v0; Rii[RMAT] = v1; Rii[2 * RMAT] = v2; Rii[3 * RMAT] = v3; Rii[4 * RMAT] = v4;
-                            const int i2 = 2 * it_i;
+                        } else {                // one-body item: minus its block in the diagonal slot of A
                             *reinterpret_cast<double2*>(A + a_row(i2) * DP + i2) = make_double2(-a00, -a01);
                             *reinterpret_cast<double2*>(A + a_row(i2 + 1) * DP + i2) = make_double2(-a01, -a11);
                         }

@@ -15,7 +15,7 @@ out = (C.c_ulonglong * 64)()
 model.local_energy(x, stash=True); lib.ff_debug_e5_cycles(C.byref(out), 1)
 model.local_energy(x, stash=True); lib.ff_debug_e5_cycles(C.byref(out), 1)
 names = {0: ["wait M free + Gram", "wait items", "row sums + y", "bar 1", "init + K.A (DMMA)", "K.u + Ks copy", "-", "owner barrier"],
-         2: ["items", "wait M", "contraction", "bar 3 + sums + L", "wait row sums", "scalars", "wait A free", "next radial functions"]}
+         2: ["A blocks (after the wait)", "wait M", "contraction", "bar 3 + sums + L", "wait row sums", "scalars", "items + wait A free", "next radial functions"]}
 nb = walkers * 64
 for obs, role in enumerate(["owner warp 0 (no Gram)", "owner warp 1", "first worker warp", "last worker warp"]):
     v = out[16 * obs:16 * obs + 16]
