@@ -86,7 +86,7 @@ def _moments(*vs):
     parts = []
     for v in vs:
         parts += [v.sum(), (v * v).sum()]
-    parts.append(torch.tensor(float(v0.numel()), device=v0.device, dtype=v0.dtype))
+    parts.append(torch.full((), float(v0.numel()), device=v0.device, dtype=v0.dtype))      # (a fill kernel, not a host-to-device copy)
     return torch.stack(parts)
 
 

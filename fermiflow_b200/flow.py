@@ -37,7 +37,8 @@ def _backward_through_flow(cnf, model, stash, B, gbar_z, gbar_delta, need_x):
     dev = gbar_z.device
     v = cnf.v
     params = _flat_params(v)
-    grads = [torch.zeros(p.numel(), dtype=torch.float64, device=dev) for p in params]
+    sizes = [p.numel() for p in params]
+    grads = list(torch.zeros(sum(sizes), dtype=torch.float64, device=dev).split(sizes))      # one fill launch
     gp = [L.ptr(g) for g in grads] + [None] * (6 - len(grads))
     grad_x = torch.empty_like(gbar_z) if need_x else None
     work = torch.empty(stash.n_work, dtype=torch.float64, device=dev)

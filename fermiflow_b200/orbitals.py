@@ -73,11 +73,22 @@ class HO2D(Orbitals):
         self.E_indices = lambda n: tuple(range(n * (n + 1) // 2, (n + 1) * (n + 2) // 2))
 
 
+_INDEX_CACHE = {}
+
+
 def orbital_indices(orbitals, device):
-    """int32 device vector of HO2D indices for a tuple of Orbital objects."""
+    """int32 device vector of HO2D indices for a tuple of Orbital objects.  The vectors are cached per (indices,
+    device): building one is a blocking host-to-device copy, and the hot path asks for the same occupations at
+    every iteration.  (Read-only: callers must not write into them.)"""
     try:
-        idx = [o.index for o in orbitals]
+        idx = tuple(int(o.index) for o in orbitals)
     except AttributeError:
         raise TypeError("orbitals must come from fermiflow_b200.orbitals.HO2D (python callables "
                         "cannot be evaluated by the CUDA kernels)")
-    return torch.tensor(idx, dtype=torch.int32, device=device)
+    key = (idx, str(torch.device(device)))
+    t = _INDEX_CACHE.get(key)
+    if t is None:
+        if len(_INDEX_CACHE) > 4096:
+            _INDEX_CACHE.clear()
+        t = _INDEX_CACHE[key] = torch.tensor(idx, dtype=torch.int32, device=device)
+    return t
