@@ -148,9 +148,10 @@ __global__ void __launch_bounds__(512) adjoint_kernel(const AdjArgs a) {
                 int w = g / D, e = g - w * D;
                 int i = e >> 1, c = e & 1;
                 const double* v = vec(w);
-                double acc = 0.0;
-                for (int j = 0; j < i; ++j) acc -= v[2 * pair_index(j, i, n) + c];
+                double acc = 0.0, accm = 0.0;                 // (same order of additions as adjoint_warp_kernel: the two agree bit for bit)
+                for (int j = 0; j < i; ++j) accm += v[2 * pair_index(j, i, n) + c];
                 for (int j = i + 1; j < n; ++j) acc += v[2 * pair_index(i, j, n) + c];
+                acc -= accm;
                 if (has_mu) acc += v[2 * (NP + i) + c];
                 if (sub > 0) ib(w, 3 - sub)[e] = acc;
                 else ubar(w)[e] += acc + ib(w, 0)[e] + ib(w, 1)[e] + ib(w, 2)[e];
@@ -267,11 +268,14 @@ __global__ void __launch_bounds__(256, 4) adjoint_warp_kernel(const AdjArgs a) {
             __syncwarp();
             for (int e = lane; e < D; e += 32) {
                 const int i = e >> 1, c = e & 1;
-                double acc = 0.0;
+                double acc = 0.0, accm = 0.0;                             // (two chains; the sums are exact reorderings of the same terms only in exact arithmetic)
                 int idx = i - 1;                                          // pair_index(0, i)
-                for (int j = 0; j < i; ++j) { acc -= vec[2 * idx + c]; idx += n - 2 - j; }
+#pragma unroll 4
+                for (int j = 0; j < i; ++j) { accm += vec[2 * idx + c]; idx += n - 2 - j; }
                 const double* vr = vec + 2 * pair_index(i, i + 1, n) + c;
+#pragma unroll 4
                 for (int j = i + 1; j < n; ++j) { acc += *vr; vr += 2; }
+                acc -= accm;
                 if (has_mu) acc += vec[2 * (NP + i) + c];
                 if (sub > 0) ib(3 - sub)[e] = acc;
                 else ubar[e] += acc + ib(0)[e] + ib(1)[e] + ib(2)[e];

@@ -187,7 +187,9 @@ __global__ void __launch_bounds__(256, FF_WARP_MINB) flow_warp_kernel(const Flow
                 const double* pU = G + 2 * (i * (2 * n - i - 1) / 2 - i - 1) + c;     // partner slot k >= i : record U_i + k + 1
                 double accm = 0.0, accp = 0.0;
                 int K = -1;                                       // K_0
+#pragma unroll 4
                 for (int k = 0; k < i; ++k) { accm += pL[2 * K]; K += n - k - 2; }
+#pragma unroll 4
                 for (int k = i; k < n - 1; ++k) accp += pU[2 * (k + 1)];
                 double v = accp - accm;
                 if (has_mu) v += G[2 * (NP + i) + c];
