@@ -98,6 +98,15 @@ int launch_finale(const ff::FlowArgs& a, const double* fin, int stride, cudaStre
 
 // Register-resident sweeps (ff_eloc5.cuh eloc5_kernel: specialised owner / worker warps; ff_eloc4.cuh eloc4_kernel under
 // option "eloc_v4") + finale kernel.
+// eloc5_kernel takes the per-SM counters, eloc4_kernel does not
+inline void launch_sweep(void (*kernel)(const ff::FlowArgs, double*, int*), unsigned grid, int threads, size_t smem, cudaStream_t st,
+                         const ff::FlowArgs& a, double* fin, int* sm_count) {
+    kernel<<<grid, threads, smem, st>>>(a, fin, sm_count);
+}
+inline void launch_sweep(void (*kernel)(const ff::FlowArgs, double*), unsigned grid, int threads, size_t smem, cudaStream_t st,
+                         const ff::FlowArgs& a, double* fin, int*) {
+    kernel<<<grid, threads, smem, st>>>(a, fin);
+}
 template <class Kernel>
 int launch_eloc_reg(Kernel kernel, int threads, size_t smem, int fin_stride, ff::FlowArgs& a, cudaStream_t st) {
     const DevInfo di = dev_info();
@@ -119,7 +128,11 @@ int launch_eloc_reg(Kernel kernel, int threads, size_t smem, int fin_stride, ff:
         }
     }
     double* fin = nullptr;
-    FF_CUDA(cudaMallocAsync((void**)&fin, (size_t)a.B * fin_stride * sizeof(double), st));
+    // (+ 1 KB behind the final states: per-SM counters by which the co-resident CTAs of eloc5_kernel tell themselves apart)
+    const size_t fin_bytes = (size_t)a.B * fin_stride * sizeof(double);
+    FF_CUDA(cudaMallocAsync((void**)&fin, fin_bytes + 1024, st));
+    FF_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(fin) + fin_bytes, 0, 1024, st));
+    int* const sm_count = reinterpret_cast<int*>(reinterpret_cast<char*>(fin) + fin_bytes);
     struct Release { double* p; cudaStream_t s; ~Release() { cudaFreeAsync(p, s); } } release{fin, st};
     FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // as many walkers per SM as registers and shared memory allow (two at N = 20, more for smaller blocks); what is left of
@@ -131,7 +144,7 @@ int launch_eloc_reg(Kernel kernel, int threads, size_t smem, int fin_stride, ff:
     const int carve = (int)std::min<long long>(100, ((long long)occ * ((long long)smem + di.smem_reserved) * 100 + di.smem_sm - 1) / di.smem_sm);
     FF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     const long long grid = std::min<long long>(a.B, (long long)di.sms * occ);
-    kernel<<<(unsigned)grid, threads, smem, st>>>(a, fin);
+    launch_sweep(kernel, (unsigned)grid, threads, smem, st, a, fin, sm_count);
     FF_LAUNCHED();
     return launch_finale(a, fin, fin_stride, st);
 }

@@ -179,6 +179,9 @@ __device__ __forceinline__ bool radial_eval_mirror(const RtHeader& T, const doub
 #ifndef FF_E5_P2P
 #define FF_E5_P2P 1
 #endif
+#ifndef FF_E5_ROT
+#define FF_E5_ROT 2          // warps by which every other CTA of an SM shifts its roles (0: off)
+#endif
 
 #ifdef FF_E5_TIMING
 __device__ unsigned long long g_e5_cyc[4][16];
@@ -188,7 +191,7 @@ __device__ unsigned long long g_e5_cyc[4][16];
 #endif
 
 template <int SN, int SMU>
-__global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_kernel(const FlowArgs a, double* __restrict__ fin) {
+__global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_kernel(const FlowArgs a, double* __restrict__ fin, int* __restrict__ sm_count) {
     extern __shared__ __align__(16) double smem[];
     constexpr Eloc5Geom G_ = eloc5_geom(SN, SMU != 0);
     constexpr int n = G_.n, D = G_.D, DP = G_.DP, NP = G_.NP, P = G_.P, NB = G_.NB;
@@ -196,12 +199,33 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
     constexpr int RP = G_.RP, RMAT = G_.RMAT;
     constexpr int kScalWarp = WW >= 3 ? 2 : WW - 1;       // worker warp that carries Delta and lapDelta
     static_assert(eloc5_supported(SN, SMU != 0), "eloc5_kernel: particle number not supported");
-    const int tid0 = threadIdx.x;
-    const bool owner0 = tid0 < NOWN;
-
     double* const S = smem;
     const double h = (a.tb - a.ta) / a.nsteps;
     const int NS = 4 * a.nsteps;
+
+    // Roles by ROTATED warp index: the NB owner warps of a CTA sit on NB consecutive warp slots, i.e. with NB = 5 two of them
+    // on the same scheduler (warp slot mod 4), and the co-resident CTA, with the same warp-slot alignment, puts its pair on
+    // that scheduler too: four tensor-core streams on one scheduler, two on each of the others.  The CTAs of an SM count
+    // themselves (an atomic on a per-SM counter behind the final-state buffer) and every other one shifts its roles by
+    // FF_E5_ROT = 2 warps: 3 + 2 + 3 + 2 streams (62.7 against 63.4 ms; shifts by 4 and 8 warps measure like none, 6 like
+    // 2 -- and ODD shifts, which put the pair on scheduler 1 or 3, 66.3 ms: the placement of the worker warps with the
+    // per-particle sums and the one-body lanes moves with them).
+    int rot = 0;
+#if FF_E5_ROT
+    if (NB == 5 && sm_count != nullptr) {
+        int* const flag = reinterpret_cast<int*>(S);
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            *flag = (atomicAdd(sm_count + smid, 1) & 1) * FF_E5_ROT;
+        }
+        __syncthreads();
+        rot = *flag;
+        __syncthreads();
+    }
+#endif
+    const int tid0 = ((int)threadIdx.x + NT - 32 * rot) % NT;
+    const bool owner0 = tid0 < NOWN;
 
     for (int e = tid0; e < G_.total; e += NT) S[e] = 0.0;                             // zero padding of the matrices and vectors, once
     // mirror of the head of the eta table (a.rt_cache_nodes rows fit behind the walker block)
