@@ -144,28 +144,6 @@ __device__ __forceinline__ double gather3(const double* __restrict__ G2, int i, 
     return acc;
 }
 
-// The same sum shared by two lanes: lane half hf takes the partners k of its parity (and hf = 0 the one-body item); the sum
-// of the two halves is gather3.
-template <int SN, int SMU>
-__device__ __forceinline__ double gather3_half(const double* __restrict__ G2, int i, int c, int hf) {
-    constexpr int n = SN, NP = SN * (SN - 1) / 2;
-    const double* pL = G2 + 3 * i + c;
-    const double* pU = G2 + 3 * (i * (2 * n - i - 1) / 2 - i - 1) + c;
-    double lo0 = 0.0, lo1 = 0.0, up0 = 0.0, up1 = 0.0;
-#pragma unroll
-    for (int q = 0; q < (n - 1 + 1) / 2; ++q) {
-        const int k = 2 * q + hf;
-        if (k < n - 1) {
-            if (k < i) { const double v = pL[3 * (k * (2 * n - k - 1) / 2 - k - 1)]; if (q & 1) lo1 += v; else lo0 += v; }
-            else { const double v = pU[3 * (k + 1)]; if (q & 1) up1 += v; else up0 += v; }
-        }
-    }
-    const double lo = lo0 + lo1, up = up0 + up1;
-    double acc = c < 2 ? up - lo : 0.5 * (up + lo);
-    if (SMU != 0 && hf == 0) acc += G2[3 * (NP + i) + c];
-    return acc;
-}
-
 // M = K^T K (upper block triangle, logical row-major) from K row-major in shared memory: the ntri blocks are dealt to
 // MW warps, NBW = ceil(ntri / MW) blocks per warp processed interleaved (2 NBW accumulator chains per warp).
 template <int SN, int SMU, int MW>

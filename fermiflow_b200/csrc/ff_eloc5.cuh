@@ -9,15 +9,17 @@
 //   * The CTA has NB owner warps and WW = ceil(P / 32) "worker" warps (N = 20: 5 + 7 = 384 threads at 80 registers,
 //     two CTAs = 24 warps per SM instead of 16).  Owners never evaluate items, workers never hold K: neither side
 //     carries the other's registers.
-//   * Two CTA barriers per RK stage, and both kinds of warps have work in both phases:
+//   * Per RK stage both kinds of warps have work in both phases, and they hand data over point to point (named barriers,
+//     see below) instead of meeting at CTA-wide barriers:
 //       phase 1   workers: finish the items of the stage from (r and the radial functions) kept in registers -- matrices R_c of the
-//                 per-particle sums, off-diagonal blocks of A = dv/dy, stash.
+//                 per-particle sums, off-diagonal blocks of A = dv/dy (stored with the step factor of the sub-stage), stash.
 //                 owners: M = K^T K on the tensor cores from the shared copy of K.
-//       phase 2   owners: row sums (k_y: y advances; u, rho, diagonal of A), K A on the tensor cores, K u, RK update of
-//                 K in registers, shared copy of the new K.
-//                 workers: contractions of their items with M, per-particle sums of those, A L, RK update of L, Delta,
-//                 lapDelta -- and then the radial functions (certified Taylor tables) of the NEXT stage at the y the
-//                 owners have just advanced: the long-latency table look-up overlaps the owners' tensor-core work.
+//       phase 2   owners: row sums (k_y: y advances; u, rho, diagonal of A), K A on the tensor cores with the RK combination
+//                 of the earlier sub-stages as the initial value of the accumulators, K u, shared copy of the new K.
+//                 workers: contractions of their items with M plus the items' share of A L, per-particle sums of those (L
+//                 advances), Delta / lapDelta as per-particle shares -- and then the radial functions (certified Taylor
+//                 tables) of the NEXT stage at the y the owners have just advanced: the long-latency table look-up
+//                 overlaps the owners' tensor-core work.
 //   * Nothing lags: M of stage s is formed in phase 1 of stage s and consumed in its phase 2.
 #pragma once
 #include "ff_eloc4.cuh"
@@ -144,29 +146,20 @@ __device__ __forceinline__ bool radial_eval_mirror(const RtHeader& T, const doub
     return true;
 }
 
-// FF_E5_RKACC: the RK combination of K enters K' = K A as the INITIAL VALUE of the tensor-core accumulators and the
+// Design notes (each was a compile-time switch while it was being measured; profiles/README.md has the numbers).
+// RK in the accumulators: the RK combination of K enters K' = K A as the INITIAL VALUE of the tensor-core accumulators and the
 // workers store A already multiplied by the stage's step factor: the new K leaves the DMMA chain finished, with
 // 0 - 2 scalar FP64 instructions per element and stage instead of 2 - 5 (rk_elem).  With K_s the input of sub-stage s of
 // the 3/8 rule and A_s' = h c_s A_s, c = (1/3, 1, 1, 1/8):
 //   K_1 = K_0 + K_0 A_0'          K_2 = (2 K_0 - K_1) + K_1 A_1'          K_3 = (2 K_1 - K_2) + K_2 A_2'
 //   K_new = (6 K_2 - K_0) / 8 + 3/8 K_3 + K_3 A_3'
 // (same polynomial in h k_1 .. h k_4 as rk_elem).  Buffer KB holds K_0, then -K_0 / 8, then (6 K_2 - K_0) / 8; KC holds K_1.
-// FF_E5_ALMMA: (A L) on the tensor cores by the worker warps (A is symmetric: one more row operand against the same
-// B fragments as K A) instead of D lanes with D-term scalar chains.
-#ifndef FF_E5_RKACC
-#define FF_E5_RKACC 1
-#endif
-// FF_E5_ALITEM: (A L) from the items instead of from the assembled matrix: (A L)_i = sum_j A_ij (L_j - L_i) + (one-body
+// A L from the items instead of from the assembled matrix: (A L)_i = sum_j A_ij (L_j - L_i) + (one-body
 // block) L_i, and the pair term changes sign with the orientation of the pair exactly like components 0, 1 of the
 // contraction records, so every item lane adds its 2-vector to those and the per-particle sums deliver k_L complete
-// (11 FP64 instructions per item lane instead of D-term chains on D lanes).
-#ifndef FF_E5_ALMMA
-#define FF_E5_ALMMA 0
-#endif
-#ifndef FF_E5_ALITEM
-#define FF_E5_ALITEM 1
-#endif
-// FF_E5_P2P: the two CTA-wide barriers of a stage become point-to-point hand-overs between the owner and the worker group
+// (11 FP64 instructions per item lane instead of D-term chains on D lanes; as one more row operand of the tensor-core
+// product it cost its full pipe time, +3 ms).
+// Hand-overs: the two CTA-wide barriers of a stage became point-to-point hand-overs between the owner and the worker group
 // (named barriers with bar.arrive on the producing and bar.sync on the consuming side, each with all NT threads of the CTA
 // as participants), so that neither group waits for the other at a place where it needs nothing from it:
 //   5  items of the stage in place (A off-diagonal, R matrices)      workers arrive, owners sync before their row sums
@@ -176,9 +169,6 @@ __device__ __forceinline__ bool radial_eval_mirror(const RtHeader& T, const doub
 //   8  contraction done: M may be overwritten                        workers arrive, owners sync before the next Gram matrix
 // (1: owners only, 3: workers only, 4: whole CTA at the walker boundaries.)  Every hand-over alternates strictly: the
 // producer of one is the consumer of another further round the cycle, so no barrier is armed twice before it completes.
-#ifndef FF_E5_P2P
-#define FF_E5_P2P 1
-#endif
 #ifndef FF_E5_ROT
 #define FF_E5_ROT 2          // warps by which every other CTA of an SM shifts its roles (0: off)
 #endif
@@ -266,9 +256,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
             if (tid0 < 8) S[G_.oScal + tid0] = 0.0;
             named_bar_sync(4, NT);
             named_bar_sync(4, NT);                       // (the workers evaluate the radial functions of stage 0)
-#if FF_E5_P2P
             named_bar_arrive(6, NT);                     // A is free for the items of stage 0
-#endif
 #ifdef FF_E5_TIMING
             const int obs = (tid0 >> 5) == 0 ? 0 : (tid0 >> 5) == 1 ? 1 : -1;
             long long tprev = clock64();
@@ -284,17 +272,11 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                 double* const Y = S + G_.oY;
                 double* const U = S + G_.oU;
                 // ======== phase 1: M = K^T K of this stage ==========================================================
-#if FF_E5_P2P
                 named_bar_sync(8, NT);                // the workers are done with the previous M
-#endif
                 if (warp >= G_.G0 && warp < G_.G0 + G_.GWN) phase_gram5<SN, SMU>(S + G_.oM, Ks, warp - G_.G0, tid & 31);
                 E5T(0);
-#if FF_E5_P2P
                 named_bar_arrive(7, NT);              // M of this stage is in place
                 named_bar_sync(5, NT);                // the items of this stage are in place
-#else
-                named_bar_sync(4, NT);
-#endif
                 E5T(1);
                 // ======== phase 2 ===================================================================================
                 // ---- per-particle sums of this stage: k_y (y advances here), u, rho, diagonal of A -----------------
@@ -339,8 +321,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                 E5T(3);
                 // ---- K' = K A on the tensor cores, k-step (rb, e): A operand = own registers -----------------------
                 double acc[NB][2];
-#if FF_E5_RKACC
-                {   // accumulators start from the RK combination of the earlier sub-stages (see FF_E5_RKACC above)
+                {   // accumulators start from the RK combination of the earlier sub-stages (see "RK in the accumulators" above)
                     double2* const PB = reinterpret_cast<double2*>(S + G_.oKB) + tid;
                     double2* const PC = reinterpret_cast<double2*>(S + G_.oKC) + tid;
 #pragma unroll
@@ -376,10 +357,6 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                     }
                     ku += ku1;
                 }
-#else
-#pragma unroll
-                for (int rn = 0; rn < NB; ++rn) { acc[rn][0] = 0.0; acc[rn][1] = 0.0; }
-#endif
                 {
                     const double* Ab = A + t4 * DP + g8;
                     double bn[NB], bc[NB];
@@ -400,10 +377,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                     }
                 }
                 E5T(4);
-#if FF_E5_P2P
                 if (stage + 1 < NS) named_bar_arrive(6, NT);       // A may be overwritten by the items of the next stage
-#endif
-#if FF_E5_RKACC
                 // ---- the accumulators ARE the new K; shared copy for the Gram matrix of the next stage -----------------
                 ku += __shfl_xor_sync(0xffffffffu, ku, 1);
                 ku += __shfl_xor_sync(0xffffffffu, ku, 2);
@@ -412,39 +386,9 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                     Kr[rn][0] = acc[rn][0]; Kr[rn][1] = acc[rn][1];
                     *reinterpret_cast<double2*>(Ks + (8 * warp + g8) * DP + 8 * rn + 2 * t4) = make_double2(Kr[rn][0], Kr[rn][1]);
                 }
-#else
-                // ---- K u (for gDelta' = -u^T J): row sums over the quad --------------------------------------------
-                double ku = 0.0;
-#pragma unroll
-                for (int rb = 0; rb < NB; ++rb) {
-                    const double2 uv = *reinterpret_cast<const double2*>(U + 8 * rb + 2 * t4);
-                    ku = fma(Kr[rb][0], uv.x, ku);
-                    ku = fma(Kr[rb][1], uv.y, ku);
-                }
-                ku += __shfl_xor_sync(0xffffffffu, ku, 1);
-                ku += __shfl_xor_sync(0xffffffffu, ku, 2);
-                // ---- RK update: K in registers, its two partials in shared memory; shared copy of the new K --------
-                double2* const PB = reinterpret_cast<double2*>(S + G_.oKB) + tid;
-                double2* const PC = reinterpret_cast<double2*>(S + G_.oKC) + tid;
-#pragma unroll
-                for (int rn = 0; rn < NB; ++rn) {
-                    double2 Bv = make_double2(0.0, 0.0), Cv = make_double2(0.0, 0.0);
-                    if (sub == 1 || sub == 2) Bv = PB[rn * NOWN];
-                    if (sub >= 1) Cv = PC[rn * NOWN];
-                    Kr[rn][0] = rk_elem(sub, Kr[rn][0], h * acc[rn][0], Bv.x, Cv.x);
-                    Kr[rn][1] = rk_elem(sub, Kr[rn][1], h * acc[rn][1], Bv.y, Cv.y);
-                    if (sub <= 1) PB[rn * NOWN] = Bv;
-                    if (sub <= 2) PC[rn * NOWN] = Cv;
-                    *reinterpret_cast<double2*>(Ks + (8 * warp + g8) * DP + 8 * rn + 2 * t4) = make_double2(Kr[rn][0], Kr[rn][1]);
-                }
-#endif
                 gd = rk_elem(sub, gd, -h * ku, gdB, gdC);
                 E5T(5);
-#if FF_E5_P2P
                 named_bar_sync(1, NOWN);              // the shared copy of the new K is complete (owners only)
-#else
-                named_bar_sync(4, NT);
-#endif
                 E5T(7);
             }
             // ---- final state to global memory: gDelta, J = K^T row-major (the workers write the vectors) -----------
@@ -519,14 +463,10 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                         const double q2 = mult * fma(f3, dd, 4.0 * f2);
                         ccq = q1 * inv_d;
                         ceq = (q2 - ccq) * inv_d2;
-#if FF_E5_RKACC
-                        // A is stored multiplied by the step factor h c_sub of this sub-stage (see FF_E5_RKACC)
+                        // A is stored multiplied by the step factor h c_sub of this sub-stage (see "RK in the accumulators")
                         const double hs = sub == 0 ? h * (1.0 / 3.0) : sub == 3 ? h * 0.125 : h;
                         const double caS = hs * ca, f0S = hs * f0;
                         a00 = fma(caS * rx, rx, f0S); a01 = caS * rx * ry; a11 = fma(caS * ry, ry, f0S);
-#else
-                        a00 = fma(ca * rx, rx, f0); a01 = ca * rx * ry; a11 = fma(ca * ry, ry, f0);
-#endif
                         const double v0 = f0 * rx, v1 = f0 * ry, v2 = ccq * rx, v3 = ccq * ry, v4 = fma(f1, dd, 2.0 * f0);
                         if (it_pair) {          // both orientations of the pair; off-diagonal blocks of A (row-permuted storage)
                             double* const Rij = R1 + it_i * RP + it_j;
@@ -541,11 +481,9 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                             Rii[0] = v0; Rii[RMAT] = v1; Rii[2 * RMAT] = v2; Rii[3 * RMAT] = v3; Rii[4 * RMAT] = v4;
                         }
                     }
-#if FF_E5_P2P
                     // (the R matrices were free since the owners' row sums; only the blocks of A have to wait for the owners' K A)
                     named_bar_sync(6, NT);            // the owners are done with the previous A
                     E5T(6);
-#endif
                     if (it_valid) {
                         const int i2 = 2 * it_i, j2 = 2 * it_j;
                         if (it_pair) {          // off-diagonal blocks of A (row-permuted storage), both orientations
@@ -559,12 +497,8 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                         }
                     }
                     E5T(0);
-#if FF_E5_P2P
                     named_bar_arrive(5, NT);          // the items of this stage are in place
                     named_bar_sync(7, NT);            // M of this stage is in place
-#else
-                    named_bar_sync(4, NT);
-#endif
                     E5T(1);
                     // ======== phase 2 ===============================================================================
                     // ---- contraction of this lane's item with M = J J^T --------------------------------------------
@@ -588,7 +522,6 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                         const double wrx = fma(w00, rx, w01 * ry), wry = fma(w01, rx, w11 * ry);
                         const double trw = w00 + w11, rwr = fma(rx, wrx, ry * wry);
                         double* const G2 = S + G_.oG2 + 3 * it_p;
-#if FF_E5_ALITEM
                         double dLx, dLy;
                         {
                             const double2 li = *reinterpret_cast<const double2*>(Lc + i2);
@@ -598,108 +531,28 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                         const double tl = ca * fma(rx, dLx, ry * dLy);
                         G2[0] = fma(ca, fma(2.0, wrx, trw * rx), cb_ * rwr * rx) + fma(f0, dLx, tl * rx);
                         G2[1] = fma(ca, fma(2.0, wry, trw * ry), cb_ * rwr * ry) + fma(f0, dLy, tl * ry);
-#else
-                        G2[0] = fma(ca, fma(2.0, wrx, trw * rx), cb_ * rwr * rx);
-                        G2[1] = fma(ca, fma(2.0, wry, trw * ry), cb_ * rwr * ry);
-#endif
                         G2[2] = fma(ccq, trw, ceq * rwr);
                     }
                     E5T(2);
-#if FF_E5_P2P
                     if (stage + 1 < NS) named_bar_arrive(8, NT);    // M may be overwritten by the next Gram matrix
-#endif
                     named_bar_sync(3, NWRK);
                     // ---- per-particle sums of the contractions: lane (particle wl / 3, component wl % 3) -----------
                     {
-#if FF_E5_ALITEM
-                        // two lanes per sum when the worker group has them (each takes the partners of one parity: half the
-                        // chain of dependent shared-memory loads and additions)
-                        constexpr bool kSplit = false && 6 * n <= NWRK;      // (measured slower at n = 20: 1890 against 1360 cycles, the predicated halves cost more than the chain)
-                        const int gl = kSplit ? (wl >> 1) : wl, hf = kSplit ? (wl & 1) : 0;
-                        const int g2_i = gl / 3, g2_k = gl - 3 * g2_i;
-                        double acc = 0.0;
-                        if (g2_i < n) acc = kSplit ? gather3_half<SN, SMU>(S + G_.oG2, g2_i, g2_k, hf) : gather3<SN, SMU>(S + G_.oG2, g2_i, g2_k);
-                        if (kSplit) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                        if (g2_i < n && hf == 0) {
-                            // components 0, 1 are k_L = A L + (d2v : M) complete (see FF_E5_ALITEM): L advances here
+                        // (two lanes per sum, each with the partners of one parity, measured slower: 1890 against 1360 cycles)
+                        const int g2_i = wl / 3, g2_k = wl - 3 * g2_i;
+                        if (g2_i < n) {
+                            const double acc = gather3<SN, SMU>(S + G_.oG2, g2_i, g2_k);
+                            // components 0, 1 are k_L = A L + (d2v : M) complete (see "A L from the items"): L advances here
                             if (g2_k < 2) {
                                 const int m = 2 * g2_i + g2_k;
                                 Ln[m] = rk_elem(sub, Lc[m], h * acc, S[G_.oLB + m], S[G_.oLC + m]);
                             } else S[G_.oP2 + g2_i] = acc;
                         }
-#else
-                        const int g2_i = wl / 3, g2_k = wl - 3 * g2_i;
-                        if (g2_i < n) {
-                            const double acc = gather3<SN, SMU>(S + G_.oG2, g2_i, g2_k);
-                            if (g2_k < 2) S[G_.oKLx + 2 * g2_i + g2_k] = acc; else S[G_.oP2 + g2_i] = acc;
-                        }
-#endif
                     }
                     E5T(3);
                     named_bar_sync(2, NT);                // the owners' sums of this stage are in place: y, A, u, rho
                     E5T(4);
-#if FF_E5_ALITEM
                     // (L' = A L + (d2v : M) came out of the per-particle sums above)
-#elif FF_E5_ALMMA
-                    // ---- L' = A L + (d2v : M) on the tensor cores: A is symmetric, so (A L)^T = L^T A is one more row
-                    // operand against the B fragments of K A; worker warp w forms the column blocks w, w + WW, ... (all
-                    // eight rows of the product are the same: lanes g8 = 0 keep columns 2 t4, 2 t4 + 1)
-                    {
-                        const int lane = tid & 31, g8 = lane >> 2, t4 = lane & 3;
-#if FF_E5_RKACC
-                        const double inv_c = sub == 0 ? 3.0 : sub == 3 ? 8.0 : 1.0, hx = h;       // A holds h c_sub A
-#else
-                        const double inv_c = h, hx = h;
-#endif
-                        for (int rn = warp - OW; rn < NB; rn += WW) {
-                            const double* Ab = A + t4 * DP + g8 + 8 * rn;
-                            double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0};
-                            double bfr[2 * NB], lfr[2 * NB];
-#pragma unroll
-                            for (int ks = 0; ks < 2 * NB; ++ks) {
-                                bfr[ks] = Ab[(8 * (ks >> 1) + 4 * (ks & 1)) * DP];
-                                lfr[ks] = Lc[8 * (ks >> 1) + 2 * t4 + (ks & 1)];
-                            }
-#pragma unroll
-                            for (int ks = 0; ks < 2 * NB; ++ks) {
-                                if (ks & 1) dmma_ordered(a1[0], a1[1], lfr[ks], bfr[ks]);
-                                else dmma_ordered(a0[0], a0[1], lfr[ks], bfr[ks]);
-                            }
-                            if (g8 == 0) {
-                                const int m = 8 * rn + 2 * t4;
-                                const double2 kx = *reinterpret_cast<const double2*>(S + G_.oKLx + m);
-                                const double2 lc = *reinterpret_cast<const double2*>(Lc + m);
-                                double2 lb = *reinterpret_cast<const double2*>(S + G_.oLB + m);
-                                double2 lcc = *reinterpret_cast<const double2*>(S + G_.oLC + m);
-                                double2 ln;
-                                ln.x = rk_elem(sub, lc.x, fma(a0[0] + a1[0], inv_c, hx * kx.x), lb.x, lcc.x);
-                                ln.y = rk_elem(sub, lc.y, fma(a0[1] + a1[1], inv_c, hx * kx.y), lb.y, lcc.y);
-                                *reinterpret_cast<double2*>(Ln + m) = ln;
-                                *reinterpret_cast<double2*>(S + G_.oLB + m) = lb;
-                                *reinterpret_cast<double2*>(S + G_.oLC + m) = lcc;
-                            }
-                        }
-                    }
-#else
-                    // ---- L' = A L + (d2v : M), lane m < D: column m of the symmetric A along the lanes -------------
-                    if (wl < D) {
-                        const double* Ac = A + wl;
-                        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-                        for (int k = 0; k < D; ++k) {
-                            const double av = Ac[a_row(k) * DP], lv = Lc[k];
-                            if ((k & 3) == 0) s0 = fma(av, lv, s0); else if ((k & 3) == 1) s1 = fma(av, lv, s1);
-                            else if ((k & 3) == 2) s2 = fma(av, lv, s2); else s3 = fma(av, lv, s3);
-                        }
-#if FF_E5_RKACC
-                        const double inv_c = sub == 0 ? 3.0 : sub == 3 ? 8.0 : 1.0;
-                        const double hkL = fma((s0 + s1) + (s2 + s3), inv_c, h * S[G_.oKLx + wl]);
-#else
-                        const double hkL = h * (((s0 + s1) + (s2 + s3)) + S[G_.oKLx + wl]);
-#endif
-                        Ln[wl] = rk_elem(sub, Lc[wl], hkL, S[G_.oLB + wl], S[G_.oLC + wl]);
-                    }
-#endif
                     // Delta' = -rho, lapDelta' = -(sum_i part2_i + u.L): the RK combination is linear, so lane i < n carries
                     // the share of particle i through all stages in registers and the shares meet once, after the sweep
                     // (a per-stage warp reduction was a 25-deep FP64 chain on the critical path of the workers)
@@ -736,17 +589,11 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
                         f0 = g[0]; f1 = g[1]; f2 = g[2]; f3 = g[3];
                     }
                 }
-#if FF_E5_P2P
                 E5T(7);
                 if (stage < 0) {
                     named_bar_sync(4, NT);            // (second barrier of the walker start: the owners wait for stage 0's radial functions)
                     named_bar_arrive(8, NT);          // M is free for the Gram matrix of stage 0
                 }
-#else
-                E5T(6);
-                named_bar_sync(4, NT);
-                E5T(7);
-#endif
             }
             // ---- final state to global memory: y, L, (Delta, lapDelta) ----------------------------------------------
             {
