@@ -15,7 +15,7 @@
 namespace ff {
 
 #ifndef FF_WARP_ILP
-#define FF_WARP_ILP 3
+#define FF_WARP_ILP 2          // items per lane and round (with the shortened table look-ups 2 measures like 3 for the values, better for the divergence sweep)
 #endif
 
 // NI items of one lane against all hidden units; coefficient rows {w1, b1, c0..c3} as in
@@ -60,7 +60,7 @@ __host__ __device__ inline WarpFlowGeom warp_flow_geom(int mode, int n, int P) {
 }
 
 #ifndef FF_WARP_MINB
-#define FF_WARP_MINB 4
+#define FF_WARP_MINB 3         // resident CTAs of 8 warps per SM the register allocation aims at (85 registers, no spills: 9.2 against 9.8 ms at 4 CTAs / 64 registers)
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(256, FF_WARP_MINB) flow_warp_kernel(const FlowArgs a) {

@@ -1,6 +1,8 @@
 """Times of the stages of one VMC iteration at N = 20 (CUDA events)."""
 import os, sys, argparse
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fermiflow_b200._lib as L0
+if os.environ.get("FF_DEV_LIB"): L0.LIB_PATH = os.path.join(os.path.dirname(L0.LIB_PATH), os.environ["FF_DEV_LIB"])
 import torch, bench
 torch.set_default_dtype(torch.float64)
 dev = torch.device("cuda:0")
