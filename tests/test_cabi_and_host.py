@@ -193,3 +193,18 @@ def test_metropolis_seed_and_rank_offset(monkeypatch):
     assert calls[2] == (8, 7, 24)
     torch.manual_seed(124)
     assert BD.FreeFermion("cpu").seed is None
+
+
+def test_orbital_index_vectors_are_cached_per_device():
+    """orbital_indices builds its int32 vector once per (occupation, device): the hot path asks for the same vectors at
+    every iteration and a fresh torch.tensor(list, device=cuda) is a blocking host-to-device copy."""
+    from fermiflow_b200 import HO2D
+    from fermiflow_b200.orbitals import orbital_indices
+    ho = HO2D()
+    a = orbital_indices(tuple(ho.orbitals[:3]) + tuple(ho.orbitals[:2]), "cpu")
+    b = orbital_indices(tuple(ho.orbitals[:3]) + tuple(ho.orbitals[:2]), torch.device("cpu"))
+    assert a is b and a.dtype == torch.int32 and a.tolist() == [0, 1, 2, 0, 1]
+    c = orbital_indices(tuple(ho.orbitals[:3]), "cpu")
+    assert c is not a and c.tolist() == [0, 1, 2]
+    with pytest.raises(TypeError):
+        orbital_indices((lambda x: x,), "cpu")
