@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(eloc5_geom(SN, SMU != 0).threads, 2) eloc5_ker
         if (threadIdx.x == 0) {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            *flag = (atomicAdd(sm_count + smid, 1) & 1) * FF_E5_ROT;
+            *flag = (atomicAdd(sm_count + (smid & 255u), 1) & 1) * FF_E5_ROT;
         }
         __syncthreads();
         rot = *flag;
